@@ -1,0 +1,310 @@
+"""ctypes binding of the CPU oracle (oracle/_build/libkmc_oracle.so) and of oracle/_ref/libref_host.so.
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs.  The product package never imports this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "_build", "libkmc_oracle.so")
+REF_LIB = os.path.join(HERE, "_ref", "libref_host.so")
+
+_pd = C.POINTER(C.c_double)
+_pi = C.POINTER(C.c_int)
+_vp = C.c_void_p
+
+
+class OrcParams(C.Structure):
+    _fields_ = [
+        ("N", C.c_int), ("nn", C.c_int), ("N_left", C.c_int), ("N_right", C.c_int), ("pbc", C.c_int),
+        ("num_metals", C.c_int), ("metals", C.c_int * 4),
+        ("lattice", C.c_double * 3),
+        ("nn_dist", C.c_double), ("sigma", C.c_double), ("k", C.c_double), ("T_bg", C.c_double),
+        ("freq", C.c_double), ("high_G", C.c_double), ("low_G", C.c_double), ("cutoff_radius", C.c_double),
+        ("Vd", C.c_double),
+        ("E_gen", C.c_double * 5), ("E_rec", C.c_double * 5), ("E_Vdiff", C.c_double * 5), ("E_Odiff", C.c_double * 5),
+        ("cg_tol_per_row", C.c_double), ("cg_max_it", C.c_int), ("spmv_lanes", C.c_int),
+    ]
+
+
+class OrcStepInfo(C.Structure):
+    _fields_ = [("cg_iterations", C.c_int), ("n_events", C.c_int), ("event_time", C.c_double),
+                ("t_charge", C.c_double), ("t_boundary", C.c_double), ("t_coulomb", C.c_double),
+                ("t_events", C.c_double)]
+
+
+def build(force: bool = False):
+    """compile the oracle (and oracle/_ref when /root/reference exists) with oracle/Makefile"""
+    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(os.path.join(HERE, "kmc_oracle.cpp")):
+        subprocess.run(["make", "-s", "-C", HERE, os.path.join(HERE, "_build", "libkmc_oracle.so")], check=True)
+    if os.path.isdir("/root/reference/src") and (force or not os.path.exists(REF_LIB)):
+        subprocess.run(["make", "-s", "-C", HERE, "ref"], check=True)
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(LIB)
+        L.orc_dot.restype = C.c_double
+        L.orc_rng_create.restype = _vp
+        L.orc_rng_next.restype = C.c_double
+        L.orc_block_sparsity.restype = C.c_long
+        L.orc_select_event.restype = C.c_long
+        _lib = L
+    return _lib
+
+
+def _i(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _d(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _p(a):
+    return a.ctypes.data_as(_vp)
+
+
+def neighbor_list(x, y, z, nn_dist=3.5, nn=52, row_start=0, row_count=None, use_cells=False):
+    x, y, z = _d(x), _d(y), _d(z)
+    N = len(x)
+    row_count = N - row_start if row_count is None else row_count
+    out = np.empty((row_count, nn), dtype=np.int32)
+    lib().orc_neighbor_list(C.c_int(N), _p(x), _p(y), _p(z), C.c_double(nn_dist), C.c_int(nn), C.c_int(row_start),
+                            C.c_int(row_count), C.c_int(int(use_cells)), _p(out))
+    return out
+
+
+def cutoff_count(element, x, y, z, cutoff=20.0, row_start=0, row_count=None):
+    element, x, y, z = _i(element), _d(x), _d(y), _d(z)
+    N = len(x)
+    row_count = N - row_start if row_count is None else row_count
+    out = np.empty(row_count, dtype=np.int32)
+    lib().orc_cutoff_count(C.c_int(N), _p(element), _p(x), _p(y), _p(z), C.c_double(cutoff), C.c_int(row_start),
+                           C.c_int(row_count), _p(out))
+    return out
+
+
+def cutoff_list(element, x, y, z, max_num_cutoff, cutoff=20.0, row_start=0, row_count=None):
+    element, x, y, z = _i(element), _d(x), _d(y), _d(z)
+    N = len(x)
+    row_count = N - row_start if row_count is None else row_count
+    out = np.empty((row_count, max_num_cutoff), dtype=np.int32)
+    lib().orc_cutoff_list(C.c_int(N), _p(element), _p(x), _p(y), _p(z), C.c_double(cutoff), C.c_int(max_num_cutoff),
+                          C.c_int(row_start), C.c_int(row_count), _p(out))
+    return out
+
+
+def block_sparsity(x, y, z, lattice, pbc, cutoff, size_i, size_j, start_i, start_j, use_cells=False):
+    x, y, z, lattice = _d(x), _d(y), _d(z), _d(lattice)
+    rp = np.zeros(size_i + 1, dtype=np.int32)
+    args = [_p(x), _p(y), _p(z), _p(lattice), C.c_int(int(pbc)), C.c_double(cutoff), C.c_int(size_i), C.c_int(size_j),
+            C.c_int(start_i), C.c_int(start_j), C.c_int(int(use_cells)), C.c_int(len(x))]
+    nnz = lib().orc_block_sparsity(*args, _p(rp), None)
+    col = np.zeros(max(nnz, 1), dtype=np.int32)
+    lib().orc_block_sparsity(*args, _p(rp), _p(col))
+    return rp, col[:nnz]
+
+
+def sparsity_K(x, y, z, lattice, pbc, nn_dist, N_left, N_right, use_cells=False):
+    """global (1-rank) K sparsity + contact blocks as initialize_sparsity_K builds them"""
+    N = len(x)
+    n = N - N_left - N_right
+    rp, col = block_sparsity(x, y, z, lattice, pbc, nn_dist, n, n, N_left, N_left, use_cells)
+    lrp, lcol = block_sparsity(x, y, z, lattice, pbc, nn_dist, n, N_left, N_left, 0, use_cells)
+    rrp, rcol = block_sparsity(x, y, z, lattice, pbc, nn_dist, n, N_right, N_left, N_left + n, use_cells)
+    return dict(row_ptr=rp, col=col, left_row_ptr=lrp, left_col=lcol, right_row_ptr=rrp, right_col=rcol)
+
+
+def update_charge(element, charge, neigh, metals, row_start=0, row_end=None):
+    element, neigh, metals = _i(element), _i(neigh), _i(metals)
+    charge = _i(charge).copy()
+    N = len(element)
+    row_end = N if row_end is None else row_end
+    lib().orc_update_charge(C.c_int(N), C.c_int(neigh.shape[-1]), _p(element), _p(charge), _p(neigh), _p(metals),
+                            C.c_int(len(metals)), C.c_int(row_start), C.c_int(row_end))
+    return charge
+
+
+def assemble_K(N, N_left, N_right, element, charge, metals, sp, Vd, high_G, low_G):
+    element, charge, metals = _i(element), _i(charge), _i(metals)
+    n = N - N_left - N_right
+    nnz = int(sp["row_ptr"][n])
+    data = np.zeros(nnz); inv_diag = np.zeros(n); rhs = np.zeros(n)
+    lib().orc_assemble_K(C.c_int(N), C.c_int(N_left), C.c_int(N_right), _p(element), _p(charge), _p(metals),
+                         C.c_int(len(metals)), _p(sp["row_ptr"]), _p(sp["col"]), _p(sp["left_row_ptr"]),
+                         _p(sp["left_col"]), _p(sp["right_row_ptr"]), _p(sp["right_col"]), C.c_double(Vd),
+                         C.c_double(high_G), C.c_double(low_G), _p(data), _p(inv_diag), _p(rhs))
+    return data, inv_diag, rhs
+
+
+def dot(u, v):
+    u, v = _d(u), _d(v)
+    return lib().orc_dot(_p(u), _p(v), C.c_long(len(u)))
+
+
+def spmv(row_ptr, col, data, x, lanes=8):
+    row_ptr, col, data, x = _i(row_ptr), _i(col), _d(data), _d(x)
+    n = len(row_ptr) - 1
+    y = np.zeros(n)
+    lib().orc_spmv(C.c_long(n), _p(row_ptr), _p(col), _p(data), _p(x), _p(y), C.c_int(lanes))
+    return y
+
+
+def pcg_jacobi(row_ptr, col, data, inv_diag, rhs, x0, tol, max_it=10000, lanes=8):
+    row_ptr, col, data, inv_diag = _i(row_ptr), _i(col), _d(data), _d(inv_diag)
+    r = _d(rhs).copy(); x = _d(x0).copy()
+    stats = np.zeros(2)
+    n = len(row_ptr) - 1
+    it = lib().orc_pcg_jacobi(C.c_long(n), _p(row_ptr), _p(col), _p(data), _p(inv_diag), _p(r), _p(x),
+                              C.c_double(tol), C.c_int(max_it), C.c_int(lanes), _p(stats))
+    return x, r, it, stats
+
+
+def coulomb(x, y, z, element, charge, sigma, k, cutoff=20.0, row_start=0, row_count=None):
+    x, y, z, element, charge = _d(x), _d(y), _d(z), _i(element), _i(charge)
+    N = len(x)
+    row_count = N - row_start if row_count is None else row_count
+    pot = np.zeros(N)
+    lib().orc_coulomb(C.c_int(N), _p(x), _p(y), _p(z), _p(element), _p(charge), C.c_double(sigma), C.c_double(k),
+                      C.c_double(cutoff), C.c_int(row_start), C.c_int(row_count), _p(pot))
+    return pot
+
+
+def build_events(neigh, layer, T_bg, freq, sigma, k, x, y, z, pot, element, charge, E, row_start=0, row_count=None):
+    neigh, layer, element, charge = _i(neigh), _i(layer), _i(element), _i(charge)
+    x, y, z, pot = _d(x), _d(y), _d(z), _d(pot)
+    N = len(x); nn = neigh.shape[-1]
+    row_count = N - row_start if row_count is None else row_count
+    typ = np.zeros(row_count * nn, dtype=np.int32)
+    prob = np.zeros(row_count * nn)
+    Es = [_d(E[k_]) for k_ in ("E_gen", "E_rec", "E_Vdiff", "E_Odiff")]
+    lib().orc_build_events(C.c_int(N), C.c_int(nn), _p(neigh), _p(layer), C.c_double(T_bg), C.c_double(freq),
+                           C.c_double(sigma), C.c_double(k), _p(x), _p(y), _p(z), _p(pot), _p(element), _p(charge),
+                           _p(Es[0]), _p(Es[1]), _p(Es[2]), _p(Es[3]), C.c_int(row_start), C.c_int(row_count),
+                           _p(typ), _p(prob))
+    return typ, prob
+
+
+class Rng:
+    def __init__(self, seed):
+        self.h = _vp(lib().orc_rng_create(C.c_uint(seed)))
+
+    def next(self):
+        return lib().orc_rng_next(self.h)
+
+    def state(self):
+        mt = np.zeros(624, dtype=np.uint32)
+        pos = C.c_int(0)
+        lib().orc_rng_get_state(self.h, _p(mt), C.byref(pos))
+        return mt, pos.value
+
+    def __del__(self):
+        try:
+            lib().orc_rng_destroy(self.h)
+        except Exception:
+            pass
+
+
+def event_loop(neigh, typ, prob, element, charge, freq, rng: Rng, max_events=0, max_log=4096):
+    neigh = _i(neigh)
+    N, nn = neigh.shape
+    typ = _i(typ).copy(); prob = _d(prob).copy(); element = _i(element).copy(); charge = _i(charge).copy()
+    log = np.zeros((max_log, 4), dtype=np.int32)
+    psum = np.zeros(max_log)
+    et = C.c_double(0)
+    n = lib().orc_event_loop(C.c_int(N), C.c_int(nn), _p(neigh), _p(typ), _p(prob), _p(element), _p(charge),
+                             C.c_double(freq), rng.h, C.c_int(max_events), C.c_int(max_log), _p(log), _p(psum),
+                             C.byref(et))
+    return dict(n_events=n, event_time=et.value, log=log[:min(n, max_log)], psum=psum[:min(n, max_log)],
+                element=element, charge=charge, prob=prob, type=typ)
+
+
+def block_scan_256(v):
+    v = _d(v)
+    out = np.zeros(256)
+    lib().orc_block_scan_256(_p(v), _p(out))
+    return out
+
+
+def select_event(prob, N, nn, number):
+    prob = _d(prob)
+    ps = C.c_double(0)
+    s = lib().orc_select_event(C.c_int(N), C.c_int(nn), _p(prob), C.c_double(number), C.byref(ps))
+    return s, ps.value
+
+
+def make_params(s, nn=52, cutoff=20.0, lanes=8) -> OrcParams:
+    """OrcParams from a product-side Structure-like object (duck typed)"""
+    p = OrcParams()
+    p.N, p.nn, p.N_left, p.N_right, p.pbc = s.N, nn, s.N_left, s.N_right, int(s.pbc)
+    p.num_metals = len(s.metals)
+    for i, m in enumerate(s.metals):
+        p.metals[i] = m
+    for i in range(3):
+        p.lattice[i] = s.lattice[i]
+    p.nn_dist, p.sigma, p.k, p.T_bg, p.freq = s.nn_dist, s.sigma, s.k, s.T_bg, s.freq
+    p.high_G, p.low_G, p.cutoff_radius, p.Vd = s.high_G, s.low_G, cutoff, s.Vd
+    for i in range(5):
+        p.E_gen[i], p.E_rec[i], p.E_Vdiff[i], p.E_Odiff[i] = (s.E["E_gen"][i], s.E["E_rec"][i], s.E["E_Vdiff"][i],
+                                                             s.E["E_Odiff"][i])
+    p.cg_tol_per_row, p.cg_max_it, p.spmv_lanes = 1e-14, 10000, lanes
+    return p
+
+
+class OracleSim:
+    """1-rank KMC simulation driven entirely by the oracle (the reference's main loop order)."""
+
+    def __init__(self, s, use_cells=False, nn=52):
+        self.s = s
+        self.p = make_params(s, nn=nn)
+        self.x, self.y, self.z = _d(s.x), _d(s.y), _d(s.z)
+        self.layer = _i(s.layer)
+        self.element = _i(s.element).copy()
+        self.charge = np.zeros(s.N, dtype=np.int32)
+        self.pot_boundary = np.zeros(s.N)
+        self.pot_total = np.zeros(s.N)
+        self.neigh = neighbor_list(self.x, self.y, self.z, 3.5, nn, use_cells=use_cells)
+        self.sp = sparsity_K(self.x, self.y, self.z, s.lattice, s.pbc, s.nn_dist, s.N_left, s.N_right, use_cells)
+        self.rng = Rng(1)
+        self.kmc_time = 0.0
+        self.step_count = 0
+
+    def superstep(self, max_log=4096):
+        info = OrcStepInfo()
+        log = np.zeros((max_log, 4), dtype=np.int32)
+        sp = self.sp
+        lib().orc_superstep(C.byref(self.p), _p(self.x), _p(self.y), _p(self.z), _p(self.layer), _p(self.neigh),
+                            _p(sp["row_ptr"]), _p(sp["col"]), _p(sp["left_row_ptr"]), _p(sp["left_col"]),
+                            _p(sp["right_row_ptr"]), _p(sp["right_col"]), _p(self.element), _p(self.charge),
+                            _p(self.pot_boundary), _p(self.pot_total), self.rng.h, C.c_int(max_log), _p(log),
+                            C.byref(info))
+        self.kmc_time += info.event_time
+        self.step_count += 1
+        return dict(step=self.step_count, event_time=info.event_time, kmc_time=self.kmc_time,
+                    n_events=info.n_events, cg_iterations=info.cg_iterations, events=log[:info.n_events].copy(),
+                    t=(info.t_charge, info.t_boundary, info.t_coulomb, info.t_events))
+
+
+# ---- reference host code (oracle/_ref) -----------------------------------------------------------
+def ref_lib():
+    build()
+    if not os.path.exists(REF_LIB):
+        return None
+    L = C.CDLL(REF_LIB)
+    L.ref_rng_create.restype = _vp
+    L.ref_rng_next.restype = C.c_double
+    L.ref_site_dist.restype = C.c_double
+    L.ref_v_solve.restype = C.c_double
+    return L
