@@ -5,9 +5,15 @@
 #include "input_parser.h"   // reference
 #include "random_num.h"     // reference
 #include "utils.h"          // reference
+#include <cstdlib>
 #include <cstring>
 
 extern "C" {
+
+// LAPACK/BLAS are absent in this image.  utils.cpp references them only from its dense gesv()/gemm() wrappers
+// (src/utils.cpp:421-428,532-538), which nothing in this shim calls; abort loudly if that ever changes.
+void dgesv_(int *, int *, double *, int *, int *, double *, int *, int *) { std::abort(); }
+void dgemv_(char *, int *, int *, double *, double *, int *, double *, int *, double *, double *, int *) { std::abort(); }
 
 struct ref_params {
     unsigned rnd_seed;

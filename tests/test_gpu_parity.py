@@ -1,0 +1,321 @@
+"""GPU parity: every stage of the hot path (through the C ABI) against the CPU oracle on the same inputs.
+Bit-exact for integer / index work; FP64 tolerances are written next to each check."""
+import gzip
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLD, make_synthetic
+
+pytestmark = pytest.mark.gpu
+
+
+def to_np(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.fixture(scope="module")
+def dev5(kmc, ctx, s5):
+    return kmc.DeviceKMC(s5, ctx=ctx)
+
+
+@pytest.fixture(scope="module")
+def orc5(orc, s5):
+    return orc.OracleSim(s5)
+
+
+# ---------------------------------------------------------------- a1 / a2 / a3: index structures, bit exact
+def test_neighbor_list_bit_exact(dev5, orc5):
+    assert (to_np(dev5.neigh) == orc5.neigh).all()
+
+
+def test_neighbor_list_row_range_and_small_nn(kmc, ctx, orc, s_small):
+    s = s_small
+    x, y, z = ctx.dev_d(s.x), ctx.dev_d(s.y), ctx.dev_d(s.z)
+    for nn, rs, rc in ((52, 0, s.N), (6, 17, 200), (3, s.N - 5, 5)):
+        got = to_np(ctx.compute_neighbor_list(x, y, z, 3.5, nn, rs, rc))
+        want = orc.neighbor_list(s.x, s.y, s.z, 3.5, nn, rs, rc)
+        assert (got == want).all()   # cap applied after ascending ordering
+
+
+def test_cutoff_size_and_list(kmc, ctx, orc, s_small):
+    s = s_small
+    x, y, z, el = ctx.dev_d(s.x), ctx.dev_d(s.y), ctx.dev_d(s.z), ctx.dev_i(s.element)
+    want = orc.cutoff_count(s.element, s.x, s.y, s.z, 20.0)
+    mx, counts = ctx.cutoff_size(el, x, y, z, 20.0, want_counts=True)
+    assert (to_np(counts) == want).all() and mx == want.max()
+    got = to_np(ctx.cutoff_list(el, x, y, z, mx))
+    assert (got == orc.cutoff_list(s.element, s.x, s.y, s.z, mx)).all()
+
+
+def test_cutoff_size_5nm(dev5, ctx, s5):
+    mx, _ = ctx.cutoff_size(dev5.element, dev5.x, dev5.y, dev5.z, 20.0)
+    assert mx == 4217   # N_cutoff of the shipped device
+
+
+def test_sparsity_K_bit_exact_5nm(dev5, orc5):
+    K = dev5.K.to_host()
+    assert dev5.K.nnz == 940008 and dev5.K.left_nnz == 2784 and dev5.K.right_nnz == 2784
+    for k in ("row_ptr", "col", "left_row_ptr", "left_col", "right_row_ptr", "right_col"):
+        assert (K[k] == orc5.sp[k]).all(), k
+
+
+@pytest.mark.parametrize("pbc", [0, 1])
+def test_sparsity_K_small_pbc_and_blocks(kmc, ctx, orc, pbc):
+    s = make_synthetic(kmc, pbc=pbc, seed=5)
+    x, y, z = ctx.dev_d(s.x), ctx.dev_d(s.y), ctx.dev_d(s.z)
+    want = orc.sparsity_K(s.x, s.y, s.z, s.lattice, pbc, s.nn_dist, s.N_left, s.N_right)
+    K = ctx.initialize_sparsity_K(x, y, z, s.lattice, pbc, s.nn_dist, s.N_left, s.N_right)
+    got = K.to_host()
+    for k in want:
+        assert (got[k] == want[k]).all(), k
+    # the reference's Distributed_matrix layout: per (rank, neighbour rank) sub-CSR with block-local columns
+    n = s.N - s.N_left - s.N_right
+    P = 3
+    counts, displs = kmc.partition(n, P)
+    for r in range(P):
+        Kr = ctx.initialize_sparsity_K(x, y, z, s.lattice, pbc, s.nn_dist, s.N_left, s.N_right, int(displs[r]), int(counts[r]))
+        for q in range(P):
+            rp, col = Kr.block_view(int(displs[q]), int(counts[q]))
+            wrp, wcol = orc.block_sparsity(s.x, s.y, s.z, s.lattice, pbc, s.nn_dist, int(counts[r]), int(counts[q]),
+                                           s.N_left + int(displs[r]), s.N_left + int(displs[q]))
+            assert (rp == wrp).all() and (col == wcol).all()
+        Kr.close()
+    K.close()
+
+
+# ---------------------------------------------------------------- a5: charges, exact
+def test_update_charge_exact(dev5, orc, s5, ctx):
+    ch = ctx.empty_i(s5.N, 0)
+    ctx.update_charge(dev5.element, ch, dev5.neigh, s5.metals)
+    want = orc.update_charge(s5.element, np.zeros(s5.N, np.int32), to_np(dev5.neigh), s5.metals)
+    got = to_np(ch)
+    assert (got == want).all()
+    assert 300 < (got != 0).sum() < 400
+
+
+# ---------------------------------------------------------------- a6: assembly, bit exact (values are +-{1,1e-8} sums)
+def test_assemble_K_bit_exact(kmc, ctx, orc, s5, dev5, orc5):
+    charge = orc.update_charge(s5.element, np.zeros(s5.N, np.int32), orc5.neigh, s5.metals)
+    # make some vacancies uncharged neighbours so the cvacancy branch is exercised
+    data, dinv, rhs = orc.assemble_K(s5.N, s5.N_left, s5.N_right, s5.element, charge, s5.metals, orc5.sp, s5.Vd,
+                                     s5.high_G, s5.low_G)
+    ctx.assemble_K(dev5.K, s5.N, s5.N_left, s5.N_right, ctx.dev_i(s5.element), ctx.dev_i(charge), s5.metals, s5.Vd,
+                   s5.high_G, s5.low_G)
+    K = dev5.K.to_host()
+    assert (K["val"] == data).all()
+    assert (K["inv_diag"] == dinv).all()
+    assert (K["rhs"] == rhs).all()
+    # algebraic invariants of the reference's postprocessing/test_matrices.py:38-48
+    import scipy.sparse as sp
+    A = sp.csr_matrix((K["val"], K["col"], K["row_ptr"]))
+    assert abs(A - A.T).max() == 0.0
+    assert (A.diagonal() > 0).all()
+
+
+# ---------------------------------------------------------------- summation spec primitives, bit exact
+def test_dot_and_spmv_bit_exact(ctx, orc, dev5, orc5, s5):
+    rng = np.random.default_rng(1)
+    for n in (1, 255, 256, 257, 36498, 100003):
+        u = rng.standard_normal(n) * 10.0 ** rng.integers(-8, 8, n)
+        v = rng.standard_normal(n)
+        assert ctx.dot(ctx.dev_d(u), ctx.dev_d(v)) == orc.dot(u, v)
+    K = dev5.K.to_host()
+    xv = rng.standard_normal(dev5.K.rows)
+    y = ctx.empty_d(dev5.K.rows)
+    ctx.spmv(dev5.K, ctx.dev_d(xv), y)
+    want = orc.spmv(K["row_ptr"], K["col"], K["val"], xv)
+    assert (to_np(y) == want).all()
+
+
+# ---------------------------------------------------------------- a7: PCG, same iteration count, bit-identical iterates
+def test_pcg_cold_start_identical(kmc, ctx, orc, s5, dev5, orc5):
+    charge = orc.update_charge(s5.element, np.zeros(s5.N, np.int32), orc5.neigh, s5.metals)
+    data, dinv, rhs = orc.assemble_K(s5.N, s5.N_left, s5.N_right, s5.element, charge, s5.metals, orc5.sp, s5.Vd,
+                                     s5.high_G, s5.low_G)
+    n = s5.N - 2 * s5.N_left
+    tol = 1e-14 * n
+    xo, ro, it_o, stats = orc.pcg_jacobi(orc5.sp["row_ptr"], orc5.sp["col"], data, dinv, rhs, np.zeros(n), tol)
+    pot = ctx.empty_d(s5.N, 0.0)
+    it_g = ctx.background_potential(dev5.K, s5.N, s5.N_left, s5.N_right, ctx.dev_i(s5.element), ctx.dev_i(charge),
+                                    s5.metals, s5.Vd, s5.high_G, s5.low_G, pot)
+    assert it_g == it_o and it_o > 100
+    got = to_np(pot)
+    assert (got[:s5.N_left] == 0).all() and (got[-s5.N_right:] == 0).all()
+    # north_star tolerance 1e-10 relative; the spec makes it bit-identical
+    assert np.abs(got[s5.N_left:-s5.N_right] - xo).max() <= 1e-10 * np.abs(xo).max()
+    assert (got[s5.N_left:-s5.N_right] == xo).all()
+    # warm start: 0 iterations
+    it2 = ctx.background_potential(dev5.K, s5.N, s5.N_left, s5.N_right, ctx.dev_i(s5.element), ctx.dev_i(charge),
+                                   s5.metals, s5.Vd, s5.high_G, s5.low_G, pot)
+    assert it2 == 0
+
+
+def test_pcg_generic_csr_random_spd(ctx, orc):
+    """dist_iterative_test shape: exported CSR + rhs, solve and compare with the oracle (main_test_cg.cpp:125-135)"""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(7)
+    n = 7302
+    A = sp.random(n, n, density=25.0 / n, random_state=3, format="csr")
+    A = A + A.T + sp.diags(np.full(n, 60.0))
+    A = A.tocsr(); A.sort_indices()
+    b = rng.standard_normal(n)
+    dinv = 1.0 / A.diagonal()
+    rp = A.indptr.astype(np.int32); col = A.indices.astype(np.int32); val = A.data
+    xo, ro, it_o, _ = orc.pcg_jacobi(rp, col, val, dinv, b, np.zeros(n), 1e-11, 500)
+    K = ctx.kmat_from_csr(ctx.dev_i(rp), ctx.dev_i(col), ctx.dev_d(val))
+    r = ctx.dev_d(b); x = ctx.empty_d(n, 0.0)
+    it_g = ctx.pcg_jacobi(K, r, x, ctx.dev_d(dinv), 1e-11, 500)
+    assert it_g == it_o
+    assert (to_np(x) == xo).all()
+    ref = sp.linalg.spsolve(A.tocsc(), b)
+    assert np.abs(to_np(x) - ref).max() < 1e-8
+    K.close()
+
+
+# ---------------------------------------------------------------- a8 / a9: Coulomb sum
+def test_coulomb_matches_oracle(ctx, orc, s5, dev5, orc5):
+    charge = orc.update_charge(s5.element, np.zeros(s5.N, np.int32), orc5.neigh, s5.metals)
+    want = orc.coulomb(s5.x, s5.y, s5.z, s5.element, charge, s5.sigma, s5.k)
+    pot = ctx.empty_d(s5.N, -1.0)
+    ctx.poisson_gridless(dev5.x, dev5.y, dev5.z, dev5.element, ctx.dev_i(charge), s5.sigma, s5.k, pot)
+    got = to_np(pot)
+    # same ascending-j summation order; only erfc differs (CUDA vs glibc, <= 2 ulp per term)
+    assert np.abs(got - want).max() <= 1e-13 * np.abs(want).max()
+    assert ctx.poisson_stats()[0] == int((charge != 0).sum())
+    # row sub-range leaves other rows untouched
+    pot2 = ctx.empty_d(s5.N, -7.0)
+    ctx.poisson_gridless(dev5.x, dev5.y, dev5.z, dev5.element, ctx.dev_i(charge), s5.sigma, s5.k, pot2, row_start=1000, row_count=500)
+    g2 = to_np(pot2)
+    assert (g2[:1000] == -7.0).all() and (g2[1500:] == -7.0).all() and (g2[1000:1500] == got[1000:1500]).all()
+    b = ctx.dev_d(np.arange(s5.N, dtype=float))
+    ctx.sum_potential(pot, b)
+    assert (to_np(pot) == got + np.arange(s5.N)).all()
+
+
+def test_coulomb_no_charges_and_mixed_signs(kmc, ctx, orc, s_small):
+    s = s_small
+    x, y, z, el = ctx.dev_d(s.x), ctx.dev_d(s.y), ctx.dev_d(s.z), ctx.dev_i(s.element)
+    pot = ctx.empty_d(s.N, 5.0)
+    ctx.poisson_gridless(x, y, z, el, ctx.empty_i(s.N, 0), s.sigma, s.k, pot)
+    assert (to_np(pot) == 0).all()
+    charge = np.zeros(s.N, np.int32)
+    charge[s.element == kmc.VACANCY] = 2
+    charge[s.element == kmc.OXYGEN_DEFECT] = -2
+    want = orc.coulomb(s.x, s.y, s.z, s.element, charge, s.sigma, s.k)
+    ctx.poisson_gridless(x, y, z, el, ctx.dev_i(charge), s.sigma, s.k, pot)
+    assert np.abs(to_np(pot) - want).max() <= 1e-12 * np.abs(want).max()
+
+
+# ---------------------------------------------------------------- a10 / a11: events
+def test_rng_stream_identical(ctx, orc, dev5):
+    dev5.ev.rng_seed(1)
+    got = dev5.ev.rng_draw(3000)
+    r = orc.Rng(1)
+    want = np.array([r.next() for _ in range(3000)])
+    assert (got == want).all()
+    mt, pos = r.state()
+    mt2, pos2 = dev5.ev.rng_get_state()
+    assert pos == pos2 and (mt == mt2).all()
+    dev5.ev.rng_seed(1)
+
+
+def test_event_rates_match_oracle(kmc, ctx, orc, s_small):
+    s = s_small
+    rng = np.random.default_rng(2)
+    sim = orc.OracleSim(s)
+    charge = orc.update_charge(s.element, np.zeros(s.N, np.int32), sim.neigh, s.metals)
+    pot = rng.uniform(-2.5, 2.5, s.N)
+    typ, prob = orc.build_events(sim.neigh, s.layer, s.T_bg, s.freq, s.sigma, s.k, s.x, s.y, s.z, pot, s.element, charge, s.E)
+    neigh = ctx.dev_i(sim.neigh.ravel()).view(s.N, 52)
+    ev = ctx.events_create(neigh)
+    ev.set_activation_energies(s.E["E_gen"], s.E["E_rec"], s.E["E_Vdiff"], s.E["E_Odiff"])
+    ev.build_event_list(neigh, ctx.dev_i(s.layer), s.T_bg, s.freq, s.sigma, s.k, ctx.dev_d(s.x), ctx.dev_d(s.y),
+                        ctx.dev_d(s.z), ctx.dev_d(pot), ctx.dev_i(s.element), ctx.dev_i(charge))
+    gp, gt = ev.event_arrays()
+    assert (gt == typ).all()
+    assert set(np.unique(typ)) >= {0, 1, 2, 3, 4}  # all four event classes + NULL are present
+    nz = prob > 0
+    assert (gp[~nz] == 0).all()
+    # exp/erfc differ by a few ulp between CUDA and glibc; rates span > 40 decades
+    assert np.abs(gp[nz] / prob[nz] - 1).max() < 1e-12
+    ev.close()
+
+
+def test_superstep_sequence_5nm_golden_and_oracle(kmc, ctx, orc, s5):
+    """6 supersteps of the shipped 5 nm run: identical events to the oracle AND to the reference's golden
+    output (snapshot_6.xyz elements, 'KMC time is:' lines to 1e-3, potentials to 5e-4 V)."""
+    dev = kmc.DeviceKMC(s5, ctx=ctx)
+    sim = orc.OracleSim(s5)
+    times = []
+    while dev.kmc_time < s5.t_switch:
+        et, ne = dev.superstep()
+        log, psum = dev.ev.log()
+        r = sim.superstep()
+        assert ne == r["n_events"] and dev.last_cg_iterations == r["cg_iterations"]
+        assert (log[:, :3] == r["events"][:, :3]).all()
+        assert abs(et - r["event_time"]) <= 1e-12 * r["event_time"]
+        times.append(dev.kmc_time)
+    assert dev.step_count == 6
+    gold_t = [2.91075e-14, 5.12158e-14, 9.36848e-14, 2.6667e-13, 9.45779e-13, 1.06019e-12]  # output1_0.txt
+    assert np.allclose(times, gold_t, rtol=1e-3)
+    with gzip.open(os.path.join(GOLD, "5nm_device", "snapshot_6.xyz.gz"), "rt") as f:
+        rows = [l.split() for l in f.read().split("\n")[2:2 + s5.N]]
+    assert [kmc.ELEMENT_NAMES[e] for e in to_np(dev.element)] == [r[0] for r in rows]
+    gp = np.array([float(r[4]) for r in rows])
+    pot = to_np(dev.pot_charge)
+    assert np.abs(pot - gp).max() < 5e-4
+    assert np.abs(pot - sim.pot_total).max() <= 1e-10 * np.abs(sim.pot_total).max()
+    assert (to_np(dev.charge) == sim.charge).all()
+
+
+def test_trajectory_1000_steps_matches_fixture(kmc, ctx, s5):
+    """north_star: identical KMC event sequence over the first 1000 steps of the 5 nm device at fixed seed
+    (fixture generated by the oracle: tests/golden/make_golden.py)."""
+    traj = json.load(open(os.path.join(GOLD, "traj_5nm.json")))
+    dev = kmc.DeviceKMC(s5, ctx=ctx)
+    for k, st in enumerate(traj["steps"]):
+        et, ne = dev.superstep()
+        log, _ = dev.ev.log()
+        assert ne == st["n_events"], f"first divergent step {k}: event count {ne} vs {st['n_events']}"
+        assert log[:, :3].tolist() == st["events"], f"first divergent step {k}"
+        assert dev.last_cg_iterations == st["cg"], f"step {k}: PCG iterations {dev.last_cg_iterations} vs {st['cg']}"
+        want = float.fromhex(st["event_time"])
+        assert abs(et - want) <= 1e-12 * want
+    fin = traj["final"]
+    assert abs(dev.kmc_time - float.fromhex(fin["kmc_time"])) <= 1e-11 * dev.kmc_time
+    assert int((to_np(dev.element) == kmc.VACANCY).sum()) == fin["n_vacancy"]
+    assert int((to_np(dev.charge) != 0).sum()) == fin["n_charged"]
+
+
+def test_event_loop_all_event_types_small(kmc, ctx, orc):
+    """synthetic device where generation / recombination / both diffusions all fire; capped event count"""
+    s = make_synthetic(kmc, seed=11, vac=0.15)
+    dev = kmc.DeviceKMC(s, ctx=ctx)
+    sim = orc.OracleSim(s)
+    seen = set()
+    for step in range(12):
+        dev.field_solve()
+        et, ne = dev.ev.execute_kmc_step(dev.neigh, dev.layer, s.T_bg, s.freq, s.sigma, s.k, dev.x, dev.y, dev.z,
+                                         dev.pot_charge, dev.element, dev.charge, max_events=40)
+        log, psum = dev.ev.log()
+        # oracle: same stages, same cap
+        sim.charge = orc.update_charge(sim.element, sim.charge, sim.neigh, s.metals)
+        data, dinv, rhs = orc.assemble_K(s.N, s.N_left, s.N_right, sim.element, sim.charge, s.metals, sim.sp, s.Vd, s.high_G, s.low_G)
+        n = s.N - s.N_left - s.N_right
+        xo, _, it, _ = orc.pcg_jacobi(sim.sp["row_ptr"], sim.sp["col"], data, dinv, rhs, sim.pot_boundary[s.N_left:s.N_left + n], 1e-14 * n)
+        sim.pot_boundary[s.N_left:s.N_left + n] = xo
+        assert it == dev.last_cg_iterations
+        pot = orc.coulomb(s.x, s.y, s.z, sim.element, sim.charge, s.sigma, s.k) + sim.pot_boundary
+        typ, prob = orc.build_events(sim.neigh, s.layer, s.T_bg, s.freq, s.sigma, s.k, s.x, s.y, s.z, pot, sim.element, sim.charge, s.E)
+        r = orc.event_loop(sim.neigh, typ, prob, sim.element, sim.charge, s.freq, sim.rng, max_events=40)
+        sim.element, sim.charge = r["element"], r["charge"]
+        assert ne == r["n_events"]
+        assert (log == r["log"]).all(), f"step {step}"
+        assert np.allclose(psum, r["psum"], rtol=1e-11, atol=0)
+        assert abs(et - r["event_time"]) <= 1e-11 * abs(r["event_time"])
+        assert (to_np(dev.element) == sim.element).all() and (to_np(dev.charge) == sim.charge).all()
+        seen |= set(log[:, 2].tolist())
+    assert seen >= {1, 2, 3}  # (generation fires in the 5 nm 1000-step fixture: 12 events)
