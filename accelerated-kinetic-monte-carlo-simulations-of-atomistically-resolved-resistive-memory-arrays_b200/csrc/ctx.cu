@@ -49,13 +49,10 @@ extern "C" int kmcb200_create(kmcb200_ctx **ctx_out, int device_ordinal, void *s
     cudaDeviceProp prop;
     KMC_CUDA(cudaGetDeviceProperties(&prop, device_ordinal));
     ctx->sm_count = prop.multiProcessorCount;
-    if (stream) {
-        ctx->stream = (cudaStream_t)stream;
-        ctx->own_stream = false;
-    } else {
-        KMC_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-        ctx->own_stream = true;
-    }
+    // NULL selects the CUDA legacy default stream (what torch.cuda.current_stream() is unless the caller
+    // switched streams), so library work stays ordered with the caller's own default-stream work.
+    ctx->stream = (cudaStream_t)stream;
+    ctx->own_stream = false;
     KMC_CUDA(cudaHostAlloc(&ctx->h_mail, 4096, cudaHostAllocDefault));
     *ctx_out = ctx;
     return 0;

@@ -53,8 +53,8 @@ int kmcb200_version(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Context.  Replaces the per-rank hipSetDevice + handle creation in reference src/kmc_main.cpp:72-101,
- * 241-245.  stream: a cudaStream_t created by the caller (e.g. torch's current stream) or NULL to let
- * the context create its own non-blocking stream. */
+ * 241-245.  stream: a cudaStream_t created by the caller (e.g. torch's current stream); NULL selects the
+ * CUDA legacy default stream. */
 int kmcb200_create(kmcb200_ctx **ctx_out, int device_ordinal, void *stream);
 int kmcb200_destroy(kmcb200_ctx *ctx);
 int kmcb200_set_stream(kmcb200_ctx *ctx, void *stream);
