@@ -75,6 +75,7 @@ _pvp = C.POINTER(C.c_void_p)
 SIGNATURES = {
     "kmcb200_last_error": (C.c_char_p, []),
     "kmcb200_version": (_i, []),
+    "kmcb200_launch_count": (_ll, []),
     "kmcb200_create": (_i, [_pvp, _i, _vp]),
     "kmcb200_destroy": (_i, [_vp]),
     "kmcb200_set_stream": (_i, [_vp, _vp]),
@@ -148,6 +149,11 @@ def load_library() -> C.CDLL:
         fn.argtypes = args
     _lib = lib
     return lib
+
+
+def launch_count() -> int:
+    """kernels launched by libkmc_b200 in this process so far"""
+    return int(load_library().kmcb200_launch_count())
 
 
 def _check(rc: int):
@@ -569,7 +575,7 @@ class Structure:
         return len(self.element)
 
 
-def load_structure(param_file: str, base_dir: Optional[str] = None) -> Structure:
+def load_structure(param_file: str, base_dir: Optional[str] = None, apply_vacancies: bool = True) -> Structure:
     """Parse parameters.txt + xyz exactly as reference src/kmc_main.cpp:117-155 does (restart or atom+interstitial
     files, makeSubstoichiometric when pristine) and attach the KMCProcess layer data."""
     p = parse_parameters(param_file)
@@ -582,7 +588,7 @@ def load_structure(param_file: str, base_dir: Optional[str] = None) -> Structure
         els.append(el); xs.append(x); ys.append(y); zs.append(z)
     el = np.ascontiguousarray(np.concatenate(els)); x = np.concatenate(xs); y = np.concatenate(ys)
     z = np.concatenate(zs)
-    if p.pristine:
+    if p.pristine and apply_vacancies:
         make_substoichiometric(el, p.initial_vacancy_concentration, p.rnd_seed)
     V = parse_parameter_vector(param_file, 0)
     t = parse_parameter_vector(param_file, 1)

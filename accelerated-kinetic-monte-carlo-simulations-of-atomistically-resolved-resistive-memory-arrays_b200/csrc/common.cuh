@@ -14,6 +14,7 @@
 #define KMC_FULL_MASK 0xffffffffu
 
 void kmc_set_error(const char *fmt, ...);
+void kmc_count_launch();  // every kernel launch of this library is counted (kmcb200_launch_count)
 
 #define KMC_CUDA(call)                                                                              \
     do {                                                                                            \

@@ -118,6 +118,7 @@ extern "C" int kmcb200_update_charge(kmcb200_ctx *ctx, const int *element, int *
     unsigned metal_mask = 0;
     for (int m = 0; m < num_metals; ++m) metal_mask |= 1u << metals_host[m];
     if (row_count == 0) return 0;
+    kmc_count_launch();
     update_charge_kernel<<<(row_count + 255) / 256, 256, 0, ctx->stream>>>(element, charge, neigh, nn, metal_mask,
                                                                           row_start, row_count);
     KMC_CUDA(cudaGetLastError());
@@ -134,6 +135,7 @@ extern "C" int kmcb200_poisson_gridless(kmcb200_ctx *ctx, int N, const double *x
     int *offs = nullptr;
     Source *src = nullptr;
     KMC_TRY(kmc_scratch(ctx, 6, (size_t)(N + 1) * sizeof(int), (void **)&offs));
+    kmc_count_launch();
     charged_flag_kernel<<<(N + 1 + 255) / 256, 256, 0, ctx->stream>>>(element, charge, N, offs);
     KMC_CUDA(cudaGetLastError());
     KMC_TRY(kmc_exclusive_scan_i32(ctx, offs, offs, (long long)N + 1, 4));  // offs[N] = Q
@@ -143,8 +145,10 @@ extern "C" int kmcb200_poisson_gridless(kmcb200_ctx *ctx, int N, const double *x
     KMC_CUDA(cudaStreamSynchronize(ctx->stream));
     Q = *(int *)ctx->h_mail;
     KMC_TRY(kmc_scratch(ctx, 7, (size_t)(Q + 1) * sizeof(Source), (void **)&src));
+    kmc_count_launch();
     charged_scatter_kernel<<<(N + 255) / 256, 256, 0, ctx->stream>>>(charge, element, x, y, z, N, offs, src);
     KMC_CUDA(cudaGetLastError());
+    kmc_count_launch();
     coulomb_kernel<<<(row_count + CT - 1) / CT, CT, 0, ctx->stream>>>(x, y, z, src, offs + N, sigma, k, cutoff_radius,
                                                                     row_start, row_count, site_potential_charge);
     KMC_CUDA(cudaGetLastError());
@@ -164,6 +168,7 @@ extern "C" int kmcb200_sum_potential(kmcb200_ctx *ctx, int N, double *site_poten
                                      const double *site_potential_boundary) {
     KMC_CHECK_ARG(ctx && site_potential_charge && site_potential_boundary && N >= 0, "arguments");
     if (N == 0) return 0;
+    kmc_count_launch();
     sum_kernel<<<(N + 255) / 256, 256, 0, ctx->stream>>>(site_potential_charge, site_potential_boundary, N);
     KMC_CUDA(cudaGetLastError());
     return 0;

@@ -13,6 +13,10 @@ void kmc_set_error(const char *fmt, ...) {
     va_end(ap);
 }
 
+static long long g_launches = 0;
+void kmc_count_launch() { ++g_launches; }
+extern "C" long long kmcb200_launch_count(void) { return g_launches; }
+
 extern "C" const char *kmcb200_last_error(void) { return g_err; }
 extern "C" int kmcb200_version(void) { return KMCB200_VERSION; }
 

@@ -521,6 +521,7 @@ extern "C" int kmcb200_events_create(kmcb200_ctx *ctx, int N, int nn, const int 
     cudaMemsetAsync(ev->rev_ptr, 0, (size_t)(N + 1) * sizeof(int), ctx->stream);
     cudaMemsetAsync(fill, 0, (size_t)(N + 1) * sizeof(int), ctx->stream);
     unsigned blocks = (unsigned)((total + 255) / 256);
+    kmc_count_launch();
     rev_count_kernel<<<blocks, 256, 0, ctx->stream>>>(neigh, total, ev->rev_ptr);
     rc = kmc_exclusive_scan_i32(ctx, ev->rev_ptr, ev->rev_ptr, (long long)N + 1, 4);
     if (rc) { kmcb200_events_destroy(ev); return rc; }
@@ -531,6 +532,7 @@ extern "C" int kmcb200_events_create(kmcb200_ctx *ctx, int N, int nn, const int 
         kmcb200_events_destroy(ev);
         return KMCB200_E_CUDA;
     }
+    kmc_count_launch();
     rev_fill_kernel<<<blocks, 256, 0, ctx->stream>>>(neigh, total, ev->rev_ptr, fill, ev->rev_slot);
     if (cudaGetLastError() != cudaSuccess) { kmc_set_error("rev_fill launch failed"); kmcb200_events_destroy(ev); return KMCB200_E_CUDA; }
     *ev_out = ev;
@@ -595,6 +597,7 @@ extern "C" int kmcb200_rng_draw(kmcb200_events *ev, int n, double *out_host) {
     if (n == 0) return 0;
     double *d = nullptr;
     KMC_TRY(kmc_scratch(ev->ctx, 9, (size_t)n * sizeof(double), (void **)&d));
+    kmc_count_launch();
     rng_draw_kernel<<<1, 32, 0, ev->ctx->stream>>>(ev->mt, n, d);
     KMC_CUDA(cudaGetLastError());
     KMC_CUDA(cudaMemcpyAsync(out_host, d, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ev->ctx->stream));
@@ -613,11 +616,13 @@ extern "C" int kmcb200_build_event_list(kmcb200_ctx *ctx, kmcb200_events *ev, in
     KMC_CHECK_ARG(ev->energies_set, "kmcb200_set_activation_energies was not called");
     const double kB = 8.617333262e-5;  // src/kmc_events.cu:5
     double kT = kB * T_bg;
+    kmc_count_launch();
     build_rates_kernel<<<(unsigned)ev->nchunk, 256, 0, ctx->stream>>>(N, nn, neigh, site_layer, kT, freq, sigma, k, x, y,
                                                                      z, site_potential_charge, site_element,
                                                                      site_charge, ev->energies, ev->prob, ev->type,
                                                                      ev->rowsum, ev->chunksum);
     KMC_CUDA(cudaGetLastError());
+    kmc_count_launch();
     super_sums_kernel<<<(unsigned)ev->nsuper, 256, 0, ctx->stream>>>(ev->chunksum, ev->nchunk, ev->supersum);
     KMC_CUDA(cudaGetLastError());
     return 0;
@@ -641,6 +646,7 @@ extern "C" int kmcb200_execute_kmc_step(kmcb200_ctx *ctx, kmcb200_events *ev, in
     a.max_events = max_events;
     a.log = ev->log; a.log_psum = ev->log_psum; a.log_cap = ev->log_cap;
     a.result = ev->result;
+    kmc_count_launch();
     event_loop_kernel<<<1, EV_THREADS, 0, ctx->stream>>>(a);
     KMC_CUDA(cudaGetLastError());
     EvResult *h = (EvResult *)ctx->h_mail;

@@ -180,11 +180,13 @@ extern "C" int kmcb200_assemble_K(kmcb200_ctx *ctx, kmcb200_kmat *K, int N, int 
         KMC_CUDA(cudaMalloc(&K->site_class, (size_t)N));
         K->site_class_cap = (size_t)N;
     }
+    kmc_count_launch();
     site_class_kernel<<<(N + 255) / 256, 256, 0, ctx->stream>>>(element, charge, N, metal_mask, K->site_class);
     KMC_CUDA(cudaGetLastError());
     constexpr int L = KMCB200_SPMV_LANES;
     long long threads = (long long)K->rows * L;
     unsigned blocks = (unsigned)((threads + 255) / 256);
+    kmc_count_launch();
     assemble_kernel<L><<<blocks, 256, 0, ctx->stream>>>(K->rows, K->row_start, N_left, K->cols_global, K->row_ptr,
                                                        K->col, K->val, K->left_row_ptr, K->left_col,
                                                        K->right_row_ptr, K->right_col, K->site_class, -Vd / 2,

@@ -229,9 +229,11 @@ int kmc_build_cellgrid(kmcb200_ctx *ctx, const double *x, const double *y, const
     g->items = items;
     if (count > 0) {
         int blocks = (count + 255) / 256;
+        kmc_count_launch();
         cell_count_kernel<<<blocks, 256, 0, ctx->stream>>>(*g, x, y, z, first, count, cid, cell_start);
         KMC_CUDA(cudaGetLastError());
         KMC_TRY(kmc_exclusive_scan_i32(ctx, cell_start, cell_start, ncell + 1, 4));
+        kmc_count_launch();
         cell_fill_kernel<<<blocks, 256, 0, ctx->stream>>>(cid, cell_start, fill, items, first, count);
         KMC_CUDA(cudaGetLastError());
     }
@@ -246,6 +248,7 @@ extern "C" int kmcb200_compute_neighbor_list(kmcb200_ctx *ctx, int N, const doub
     KMC_CHECK_ARG(row_start >= 0 && row_count >= 0 && row_start + row_count <= N, "row range");
     CellGridDev g;
     KMC_TRY(kmc_build_cellgrid(ctx, x, y, z, 0, N, nn_dist, 0, nullptr, &g));
+    kmc_count_launch();
     neighbor_kernel<<<(N + 127) / 128, 128, 0, ctx->stream>>>(g, x, y, z, N, nn_dist, nn, row_start, row_count,
                                                             neigh_out);
     KMC_CUDA(cudaGetLastError());
@@ -262,6 +265,7 @@ extern "C" int kmcb200_cutoff_size(kmcb200_ctx *ctx, int N, const int *element, 
     int *d_max = nullptr;
     KMC_TRY(kmc_scratch(ctx, 5, 64, (void **)&d_max));
     KMC_CUDA(cudaMemsetAsync(d_max, 0, sizeof(int), ctx->stream));
+    kmc_count_launch();
     cutoff_count_kernel<<<(N + 127) / 128, 128, 0, ctx->stream>>>(g, element, x, y, z, N, cutoff_radius, row_start,
                                                                 row_count, counts_out, d_max);
     KMC_CUDA(cudaGetLastError());
@@ -276,6 +280,7 @@ extern "C" int kmcb200_cutoff_list(kmcb200_ctx *ctx, int N, const int *element, 
     KMC_CHECK_ARG(ctx && element && x && y && z && cutoff_idx_out, "null pointer");
     KMC_CHECK_ARG(row_start >= 0 && row_count >= 0 && row_start + row_count <= N && max_num_cutoff >= 0, "range");
     if (row_count == 0 || max_num_cutoff == 0) return 0;
+    kmc_count_launch();
     cutoff_list_kernel<<<(row_count + 127) / 128, 128, 0, ctx->stream>>>(element, x, y, z, N, cutoff_radius,
                                                                        max_num_cutoff, row_start, row_count,
                                                                        cutoff_idx_out);
@@ -312,6 +317,7 @@ extern "C" int kmcb200_initialize_sparsity_K(kmcb200_ctx *ctx, int N, const doub
     cudaMemsetAsync(K->left_row_ptr, 0, rp_bytes, ctx->stream);
     cudaMemsetAsync(K->right_row_ptr, 0, rp_bytes, ctx->stream);
     int blocks = (row_count + 127) / 128;
+    kmc_count_launch();
     ksparsity_count_kernel<<<blocks, 128, 0, ctx->stream>>>(g, x, y, z, N, N_left, N_right, pbc, nn_dist, row_start,
                                                           row_count, K->row_ptr, K->left_row_ptr, K->right_row_ptr);
     if (cudaGetLastError() != cudaSuccess) { kmc_set_error("ksparsity_count launch failed"); return fail(KMCB200_E_CUDA); }
@@ -336,6 +342,7 @@ extern "C" int kmcb200_initialize_sparsity_K(kmcb200_ctx *ctx, int N, const doub
     int *d_ovf = nullptr;
     if ((rc = kmc_scratch(ctx, 5, 64, (void **)&d_ovf))) return fail(rc);
     cudaMemsetAsync(d_ovf, 0, sizeof(int), ctx->stream);
+    kmc_count_launch();
     ksparsity_fill_kernel<<<blocks, 128, 0, ctx->stream>>>(g, x, y, z, N, N_left, N_right, pbc, nn_dist, row_start,
                                                          row_count, K->row_ptr, K->left_row_ptr, K->right_row_ptr,
                                                          K->col, K->left_col, K->right_col, d_ovf);
@@ -358,6 +365,7 @@ extern "C" int kmcb200_kmat_block_view(kmcb200_kmat *K, int col_start, int col_c
     kmcb200_ctx *ctx = K->ctx;
     int blocks = (K->rows + 127) / 128;
     KMC_CUDA(cudaMemsetAsync(row_ptr_out, 0, (size_t)(K->rows + 1) * sizeof(int), ctx->stream));
+    kmc_count_launch();
     block_view_count_kernel<<<blocks, 128, 0, ctx->stream>>>(K->row_ptr, K->col, K->rows, col_start, col_count, row_ptr_out);
     KMC_CUDA(cudaGetLastError());
     KMC_TRY(kmc_exclusive_scan_i32(ctx, row_ptr_out, row_ptr_out, K->rows + 1, 4));
@@ -366,6 +374,7 @@ extern "C" int kmcb200_kmat_block_view(kmcb200_kmat *K, int col_start, int col_c
     KMC_CUDA(cudaStreamSynchronize(ctx->stream));
     *nnz_host = tot;
     if (col_out) {
+        kmc_count_launch();
         block_view_fill_kernel<<<blocks, 128, 0, ctx->stream>>>(K->row_ptr, K->col, K->rows, col_start, col_count,
                                                               row_ptr_out, col_out);
         KMC_CUDA(cudaGetLastError());

@@ -215,6 +215,7 @@ int ensure_cg_workspace(kmcb200_ctx *ctx, long long nchunks) {
 int kmc_spmv_launch(kmcb200_ctx *ctx, kmcb200_kmat *K, const double *xg, double *y, bool with_dot) {
     constexpr int L = KMCB200_SPMV_LANES;
     unsigned blocks = (unsigned)((K->rows + CH - 1) / CH);
+    kmc_count_launch();
     if (with_dot)
         spmv_kernel<L, true><<<blocks, CH, 0, ctx->stream>>>(K->rows, K->row_ptr, K->col, K->val, xg, K->row_start, y,
                                                             ctx->partials, ctx->cg_state);
@@ -242,6 +243,7 @@ extern "C" int kmcb200_dot(kmcb200_ctx *ctx, const double *u, const double *v, l
     long long nchunks = (n + CH - 1) / CH;
     if (nchunks == 0) nchunks = 1;
     KMC_TRY(ensure_cg_workspace(ctx, nchunks));
+    kmc_count_launch();
     dot_kernel<<<(unsigned)nchunks, CH, 0, ctx->stream>>>(n, u, v, ctx->partials, ctx->cg_state);
     KMC_CUDA(cudaGetLastError());
     KMC_CUDA(cudaMemcpyAsync(ctx->h_mail, &ctx->cg_state->scalar_out, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -271,6 +273,7 @@ extern "C" int kmcb200_pcg_jacobi(kmcb200_ctx *ctx, kmcb200_kmat *K, double *r_l
     KMC_CUDA(cudaMemcpyAsync(st, h, sizeof(CgState), cudaMemcpyHostToDevice, ctx->stream));
     // A*x0 (:191), residual + preconditioned residual + both setup dots (:187-213)
     KMC_TRY(kmc_spmv_launch(ctx, K, x_local, K->Ap, false));
+    kmc_count_launch();
     cg_init_kernel<<<nchunks, CH, 0, ctx->stream>>>(rows, r_local, K->Ap, diag_inv_local, K->z, ctx->partials, st);
     KMC_CUDA(cudaGetLastError());
     int *h_flags = (int *)((char *)ctx->h_mail + 512);
@@ -284,8 +287,10 @@ extern "C" int kmcb200_pcg_jacobi(kmcb200_ctx *ctx, kmcb200_kmat *K, double *r_l
     const unsigned eb = (unsigned)((rows + 255) / 256);
     while (!h_flags[2]) {  // done
         for (int b = 0; b < batch; ++b) {
+            kmc_count_launch();
             cg_pupdate_kernel<<<eb, 256, 0, ctx->stream>>>(rows, K->row_start, K->z, K->p_full, st);
             KMC_TRY(kmc_spmv_launch(ctx, K, K->p_full, K->Ap, true));
+            kmc_count_launch();
             cg_update_kernel<<<nchunks, CH, 0, ctx->stream>>>(rows, K->row_start, K->p_full, K->Ap, diag_inv_local,
                                                              x_local, r_local, K->z, ctx->partials, st);
         }

@@ -70,14 +70,17 @@ int scan_rec(kmcb200_ctx *ctx, const int *in, int *out, long long n, int *work, 
     long long tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
     if (tiles <= 0) return 0;
     if (tiles == 1) {
+        kmc_count_launch();
         scan_tiles<<<1, SCAN_THREADS, 0, ctx->stream>>>(in, out, nullptr, n);
         KMC_CUDA(cudaGetLastError());
         return 0;
     }
     int *tile_sums = work;
+    kmc_count_launch();
     scan_tiles<<<(unsigned)tiles, SCAN_THREADS, 0, ctx->stream>>>(in, out, tile_sums, n);
     KMC_CUDA(cudaGetLastError());
     KMC_TRY(scan_rec(ctx, tile_sums, tile_sums, tiles, work + tiles, level + 1));
+    kmc_count_launch();
     add_tile_offsets<<<(unsigned)tiles, SCAN_THREADS, 0, ctx->stream>>>(out, tile_sums, n);
     KMC_CUDA(cudaGetLastError());
     return 0;
@@ -142,6 +145,7 @@ int kmc_bbox(kmcb200_ctx *ctx, const double *x, const double *y, const double *z
     if (count > 0) {
         int blocks = (count + 255) / 256;
         if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
+        kmc_count_launch();
         bbox_kernel<<<blocks, 256, 0, ctx->stream>>>(x, y, z, first, count, d6);
         KMC_CUDA(cudaGetLastError());
     }

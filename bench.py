@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""bench.py -- KMC steps/s of the field-solve + event-selection hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle port on the host cores
+
+Workload (config.workload): BASELINE.json configs[1], "structures/40nm_crossbar full KMC run after
+initialization, 1 B200".  The 40 nm xyz files are not shipped with the reference, so the stand-in of
+SURVEY.md section 8(d) is used: 8x8 lateral tiling of the shipped 5 nm cell (N = 2 409 600 sites,
+num_atoms_first_layer = 36 864, V = 15 V, Device seed 32, KMC seed 1), random-free synthetic data otherwise
+identical in format to the reference's inputs.  A "step" is one KMC superstep: update_charge ->
+K assembly + Jacobi-PCG -> screened Coulomb sum -> potential sum -> event rates + residence-time loop
+(reference src/kmc_main.cpp:328-540).  Inputs (~0.5 GB matrix + 1 GB event list per step) are far larger
+than L2 (126 MB), so no L2 flush is needed between timed steps.
+
+One JSON line on stdout (rank 0).  See the repo's DESIGN.md section 7 for every key.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+PKG = "accelerated-kinetic-monte-carlo-simulations-of-atomistically-resolved-resistive-memory-arrays_b200"
+PARAM_5NM = os.path.join(ROOT, "tests", "golden", "5nm_device", "parameters.txt")
+COUNTERS = os.path.join(ROOT, "profiles", "workload_counters.json")
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """samples nvidia-smi SM clocks + throttle reasons during the timed region"""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([v.strip() for v in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(sm)}
+
+
+def build_workload(kmc, name):
+    syn = importlib.import_module(PKG + ".synthetic")
+    if name == "5nm":
+        return kmc.load_structure(PARAM_5NM), "structures/5nm_device (shipped), N=37650"
+    t = {"standin8x8": 8, "standin4x4": 4, "standin2x2": 2, "standin16x16": 16}[name]
+    s = syn.crossbar_standin(PARAM_5NM, t, t, order="file", Vd=15.0, rnd_seed=32)
+    return s, (f"40nm_crossbar stand-in: {t}x{t} lateral tiling of the shipped 5nm cell, N={s.N}, "
+               f"num_atoms_first_layer={s.N_left}, Vd=15, file order")
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (the reference has no CPU implementation of this path)
+# ------------------------------------------------------------------------------------------------
+def cpu_step_cost(orc, s, state, cg_iters_per_step, events_per_step, coulomb_row_stride=128):
+    """times the oracle stages of ONE superstep of workload `s` from `state`; bounded: the PCG is charged as
+    (1 + cg_iters_per_step) SpMV+dot+axpy iterations measured on 2 iterations, the Coulomb sum runs on every
+    coulomb_row_stride-th row block and is scaled, the event loop runs events_per_step events."""
+    N = s.N
+    n = N - s.N_left - s.N_right
+    el, ch = state["element"].copy(), state["charge"].copy()
+    t = {}
+    t0 = time.perf_counter()
+    ch = orc.update_charge(el, ch, state["neigh"], s.metals)
+    t["charge"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    data, dinv, rhs = orc.assemble_K(N, s.N_left, s.N_right, el, ch, s.metals, state["sp"], s.Vd, s.high_G, s.low_G)
+    t["assemble"] = time.perf_counter() - t0
+    sp = state["sp"]
+    x0 = state["pot_boundary"][s.N_left:s.N_left + n]
+    t0 = time.perf_counter()
+    orc.pcg_jacobi(sp["row_ptr"], sp["col"], data, dinv, rhs, x0, 0.0, 2)   # tol 0 -> exactly 2 iterations
+    t2 = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    orc.pcg_jacobi(sp["row_ptr"], sp["col"], data, dinv, rhs, x0, 1e300, 2)  # tol huge -> setup only (A x0, 2 dots)
+    t_setup = time.perf_counter() - t0
+    t_iter = max((t2 - t_setup) / 2, 0.0)
+    t["pcg"] = t_setup + cg_iters_per_step * t_iter
+    rows = max(1, N // coulomb_row_stride)
+    t0 = time.perf_counter()
+    orc.coulomb(s.x, s.y, s.z, el, ch, s.sigma, s.k, 20.0, 0, rows)
+    # rows are not uniform in work (contacts see nothing): sample a middle block as well
+    orc.coulomb(s.x, s.y, s.z, el, ch, s.sigma, s.k, 20.0, N // 2, rows)
+    t["coulomb"] = (time.perf_counter() - t0) * (N / (2.0 * rows))
+    t0 = time.perf_counter()
+    typ, prob = orc.build_events(state["neigh"], s.layer, s.T_bg, s.freq, s.sigma, s.k, s.x, s.y, s.z,
+                                 state["pot_total"], el, ch, s.E)
+    t["rates"] = time.perf_counter() - t0
+    rng = orc.Rng(1)
+    t0 = time.perf_counter()
+    orc.event_loop(state["neigh"], typ, prob, el, ch, s.freq, rng, max_events=max(1, int(round(events_per_step))),
+                   max_log=16)
+    t["events"] = time.perf_counter() - t0
+    return t
+
+
+def oracle_state(orc, s):
+    neigh = orc.neighbor_list(s.x, s.y, s.z, 3.5, 52, use_cells=True)
+    sp = orc.sparsity_K(s.x, s.y, s.z, s.lattice, s.pbc, s.nn_dist, s.N_left, s.N_right, use_cells=True)
+    return {"neigh": neigh, "sp": sp, "element": s.element.copy(), "charge": np.zeros(s.N, np.int32),
+            "pot_boundary": np.zeros(s.N), "pot_total": np.zeros(s.N)}
+
+
+def run_reference(args):
+    """--impl reference: the oracle port timed on the host cores (no GPU), bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    kmc = importlib.import_module(PKG)
+    from oracle import binding as orc
+    s, desc = build_workload(kmc, args.workload)
+    counters = {"cg_iters_per_step": 0.0, "events_per_step": 1.0}
+    if os.path.exists(COUNTERS):
+        counters.update(json.load(open(COUNTERS)).get(args.workload, {}))
+    st = oracle_state(orc, s)
+    times = []
+    for k in range(args.warmup + args.steps):
+        t = cpu_step_cost(orc, s, st, counters["cg_iters_per_step"], counters["events_per_step"])
+        if k >= args.warmup:
+            times.append(sum(t.values()))
+    ms = 1e3 * float(np.mean(times))
+    val = 1e3 / ms
+    cores = orc.lib().orc_num_threads()
+    sample = (f"oracle port (C++/OpenMP restatement of the reference GPU algorithm; the reference has no CPU code for "
+              f"this path): per step full update_charge + full K assembly + PCG setup + {counters['cg_iters_per_step']:.1f} "
+              f"PCG iterations (cost measured on 2) + Coulomb sum on 2/128 of the rows scaled to N + full rate list + "
+              f"{counters['events_per_step']:.0f} events")
+    line = {"impl": "reference", "metric": "kmc_steps_per_sec", "value": val, "unit": "steps/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc, "per_step_counters": counters},
+            "cpu_baseline": {"value": val, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    kmc = importlib.import_module(PKG)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference "
+                         "for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    s, desc = build_workload(kmc, args.workload)
+    ctx = kmc.Context(local_rank)
+    t_setup0 = time.perf_counter()
+    if world > 1:
+        par = importlib.import_module(PKG + ".multigpu")
+        sim = par.DistributedDeviceKMC(s, ctx=ctx, rank=rank, world=world)
+    else:
+        sim = kmc.DeviceKMC(s, ctx=ctx)
+    ctx.sync()
+    t_setup = time.perf_counter() - t_setup0
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (first superstep = cold PCG from a zero guess) --------------------------------------
+    per_step = []
+    for _ in range(args.warmup):
+        et, ne = sim.superstep()
+        per_step.append((sim.last_cg_iterations, ne))
+    # ---- timed region: K supersteps, device resident ----------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = kmc.launch_count()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    timed = []
+    for _ in range(args.steps):
+        et, ne = sim.superstep()
+        timed.append((sim.last_cg_iterations, ne))
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = kmc.launch_count() - launches0
+    if world > 1:
+        tt = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_total = float(tt.item())
+    ms_per_step = ms_total / args.steps
+    value = 1e3 / ms_per_step
+
+    # ---- e2e: same supersteps through the host-buffer API (H2D of the mutable site state from pinned host memory,
+    #      D2H of element/charge/potential every step), reference GPUBuffers::sync_HostToGPU/GPUToHost -------------
+    N = s.N
+    h_el = torch.empty(N, dtype=torch.int32).pin_memory()
+    h_ch = torch.empty(N, dtype=torch.int32).pin_memory()
+    h_pot = torch.empty(N, dtype=torch.float64).pin_memory()
+    h_el.copy_(sim.element); h_ch.copy_(sim.charge)
+    torch.cuda.synchronize()
+    e2e_steps = max(1, args.steps)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        sim.element.copy_(h_el, non_blocking=True)
+        sim.charge.copy_(h_ch, non_blocking=True)
+        sim.superstep()
+        h_el.copy_(sim.element, non_blocking=True)
+        h_ch.copy_(sim.charge, non_blocking=True)
+        h_pot.copy_(sim.pot_charge, non_blocking=True)
+        torch.cuda.synchronize()
+    barrier()
+    e2e_ms = 1e3 * (time.perf_counter() - t0) / e2e_steps
+    if world > 1:
+        tt = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_ms = float(tt.item())
+    if rank == 0:
+        sampler.stop_flag = True
+
+    # ---- stage breakdown + roofline of the PCG hot kernel (SpMV with fused p.Ap), CUDA events on the library stream
+    def time_ms(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    stages = {}
+    roof = None
+    if world == 1:
+        K = sim.K
+        n = K.rows
+        xv = ctx.empty_d(n, 1.0)
+        yv = ctx.empty_d(n, 0.0)
+        t_spmv = time_ms(lambda: ctx.spmv(K, xv, yv), 20)
+        spmv_bytes = 12.0 * K.nnz + 20.0 * n           # val 8 + col 4 per nnz; row_ptr 4 + y 8 + x 8 per row
+        peak, peak_src = hbm_peak()
+        ach = spmv_bytes / (t_spmv * 1e-3) / 1e9
+        roof = {"kernel": "spmv_kernel<8> (CSR SpMV, fused p.Ap partials)", "bound": "hbm", "achieved": ach,
+                "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": spmv_bytes, "ms_per_launch": t_spmv}
+        try:
+            prof = json.load(open(os.path.join(ROOT, "profiles", "spmv_traffic.json")))
+            roof["traffic"] = prof.get(args.workload, {}).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        el2, ch2 = sim.element.clone(), sim.charge.clone()
+        stages["update_charge_ms"] = time_ms(lambda: ctx.update_charge(el2, ch2, sim.neigh, s.metals), 5)
+        stages["assemble_K_ms"] = time_ms(lambda: ctx.assemble_K(K, N, s.N_left, s.N_right, el2, ch2, s.metals, s.Vd,
+                                                                 s.high_G, s.low_G), 5)
+        stages["assemble_K_GBs"] = (12.0 * K.nnz + 36.0 * n) / (stages["assemble_K_ms"] * 1e-3) / 1e9
+        pc = ctx.empty_d(N, 0.0)
+        stages["coulomb_ms"] = time_ms(lambda: ctx.poisson_gridless(sim.x, sim.y, sim.z, el2, ch2, s.sigma, s.k, pc), 3)
+        q, pairs = ctx.poisson_stats()
+        stages["coulomb_charged_sources"] = q
+        stages["coulomb_pair_tests_per_s"] = pairs / (stages["coulomb_ms"] * 1e-3)
+        stages["build_event_list_ms"] = time_ms(lambda: sim.ev.build_event_list(sim.neigh, sim.layer, s.T_bg, s.freq, s.sigma,
+                                                                                s.k, sim.x, sim.y, sim.z, sim.pot_charge,
+                                                                                el2, ch2), 3)
+        stages["spmv_ms"] = t_spmv
+        stages["spmv_GBs"] = ach
+        u, v = ctx.empty_d(n, 1.0), ctx.empty_d(n, 2.0)
+        stages["dot_ms"] = time_ms(lambda: ctx.dot(u, v), 10)
+
+    cg_per_step = float(np.mean([c for c, _ in timed]))
+    ev_per_step = float(np.mean([e for _, e in timed]))
+
+    # ---- CPU baseline (rank 0, N = 1): the oracle port on the box's host cores, bounded sample -------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import binding as orc
+        st = oracle_state(orc, s)
+        st["element"] = sim.element.cpu().numpy()
+        st["charge"] = sim.charge.cpu().numpy()
+        st["pot_boundary"] = sim.pot_boundary.cpu().numpy()
+        st["pot_total"] = sim.pot_charge.cpu().numpy()
+        t = cpu_step_cost(orc, s, st, cg_per_step, ev_per_step)
+        tot = sum(t.values())
+        cpu = {"value": 1.0 / tot, "unit": "steps/s", "cores": orc.lib().orc_num_threads(), "kind": "port",
+               "sample": (f"oracle port (the reference has no CPU code for this path): one superstep of the same workload "
+                          f"from the post-timing state: full update_charge + full K assembly + PCG setup + "
+                          f"{cg_per_step:.1f} PCG iterations (cost measured on 2) + Coulomb sum on 2/128 of the rows "
+                          f"scaled to N + full rate list + {ev_per_step:.0f} events"),
+               "stage_seconds": {k: round(v, 4) for k, v in t.items()}}
+
+    if rank == 0:
+        line = {"metric": "kmc_steps_per_sec", "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": desc, "l2_policy": "inputs (matrix + event list) >> L2; no flush needed",
+                           "cg_iterations_per_step": cg_per_step, "events_per_step": ev_per_step,
+                           "warmup_counters": per_step, "setup_s": round(t_setup, 2),
+                           "K_rows": int(sim.K.rows), "K_nnz": int(sim.K.nnz)},
+                "e2e": {"value": 1e3 / e2e_ms, "unit": "steps/s", "ms_per_step": e2e_ms,
+                        "h2d_bytes_per_step": 8 * N, "d2h_bytes_per_step": 16 * N},
+                "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roof, "stages": stages,
+                "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+        if args.write_counters:
+            os.makedirs(os.path.dirname(COUNTERS), exist_ok=True)
+            allc = json.load(open(COUNTERS)) if os.path.exists(COUNTERS) else {}
+            allc[args.workload] = {"cg_iters_per_step": cg_per_step, "events_per_step": ev_per_step}
+            json.dump(allc, open(COUNTERS, "w"), indent=1)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("KMC_BENCH_WORKLOAD", "standin8x8"))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--write-counters", action="store_true", help="record per-step PCG/event counters for the CPU arm")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -50,6 +50,8 @@ typedef struct kmcb200_events kmcb200_events;  /* event list workspace + KMC RNG
 
 const char *kmcb200_last_error(void);
 int kmcb200_version(void);
+/* number of CUDA kernels this library has launched in this process (bench.py reports the delta) */
+long long kmcb200_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Context.  Replaces the per-rank hipSetDevice + handle creation in reference src/kmc_main.cpp:72-101,
