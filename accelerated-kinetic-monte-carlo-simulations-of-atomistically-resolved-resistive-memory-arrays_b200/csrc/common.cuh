@@ -60,6 +60,7 @@ struct kmcb200_ctx {
     void *h_mail = nullptr;
     // coulomb statistics of the last call
     long long last_num_charged = 0, last_pair_tests = 0;
+    void *pair_counter_dev = nullptr;
     // dot/pcg workspace
     CgState *cg_state = nullptr;  // device
     double *partials = nullptr;   // device, 2 * max chunks

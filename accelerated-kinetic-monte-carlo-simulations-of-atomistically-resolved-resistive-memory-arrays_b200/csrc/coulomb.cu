@@ -7,7 +7,7 @@
 // ascending site order each step and an N x Q kernel tiles them through shared memory; the membership test of
 // the cutoff list (element class, r < cutoff, i != j) is evaluated inline, and every site sums its sources in
 // ascending j like the reference thread does.
-#include "common.cuh"
+#include "cellgrid.cuh"
 
 namespace {
 
@@ -58,36 +58,109 @@ struct __align__(16) Source {
 __global__ void charged_scatter_kernel(const int *__restrict__ charge, const int *__restrict__ element,
                                        const double *__restrict__ x, const double *__restrict__ y,
                                        const double *__restrict__ z, int N, const int *__restrict__ offs,
-                                       Source *__restrict__ src) {
+                                       const int *__restrict__ site_cell, Source *__restrict__ src,
+                                       int *__restrict__ src_cell) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     if (charge[i] != 0 && kmc_possibly_charged(element[i])) {
         Source s;
         s.x = x[i]; s.y = y[i]; s.z = z[i]; s.charge = charge[i]; s.idx = i;
-        src[offs[i]] = s;
+        int o = offs[i];
+        src[o] = s;
+        src_cell[o] = site_cell[i];
     }
 }
 
+// order-sensitive 64-bit checksum of the coordinates: guards the cached target plan against a caller that reuses
+// the same device address for a different structure
+__global__ void pos_checksum_kernel(const double *__restrict__ x, const double *__restrict__ y,
+                                    const double *__restrict__ z, int N, unsigned long long *__restrict__ out) {
+    unsigned long long h = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+        unsigned long long a = (unsigned long long)__double_as_longlong(x[i]);
+        unsigned long long b = (unsigned long long)__double_as_longlong(y[i]);
+        unsigned long long c = (unsigned long long)__double_as_longlong(z[i]);
+        h += (a * 0x9E3779B97F4A7C15ull + (b ^ (c << 1))) * (2ull * (unsigned long long)i + 1ull);
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) h += __shfl_xor_sync(KMC_FULL_MASK, h, off);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, h);
+}
+
+// ---- static target plan: sites grouped by 20 A cell -------------------------------------------------------
+__global__ void site_cell_kernel(CellGridDev g, const double *__restrict__ x, const double *__restrict__ y,
+                                 const double *__restrict__ z, int N, int *__restrict__ site_cell) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) site_cell[i] = g.cell(g.cx(x[i]), g.cy(y[i]), g.cz(z[i]));
+}
+__global__ void cell_blocks_kernel(const int *__restrict__ cell_start, int ncell, int ct, int *__restrict__ nblk) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c <= ncell) nblk[c] = (c < ncell) ? (cell_start[c + 1] - cell_start[c] + ct - 1) / ct : 0;
+}
+__global__ void block_map_kernel(const int *__restrict__ blk_start, int ncell, int *__restrict__ blk_cell) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncell) return;
+    for (int b = blk_start[c]; b < blk_start[c + 1]; ++b) blk_cell[b] = c;
+}
+
+// ---- per step: ascending-j list of the charged sources in the 27-cell neighbourhood of every cell ----------
+// One thread per cell walks the (ascending j) compacted source list; every lane of a warp reads the same source
+// cell id (broadcast), so the walk costs one L1 hit per source.
+template <bool FILL>
+__global__ void __launch_bounds__(128) cell_sources_kernel(int nx, int ny, int nz, const int *__restrict__ src_cell,
+                                                          const int *__restrict__ nsrc_ptr,
+                                                          const int *__restrict__ cell_tstart,
+                                                          int *__restrict__ cnt_or_start, int *__restrict__ lists) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    int ncell = nx * ny * nz;
+    bool active = c < ncell && (cell_tstart[c + 1] > cell_tstart[c]);  // cells without targets need no list
+    int cc = c < ncell ? c : 0;
+    int a = cc / (ny * nz), b = (cc / nz) % ny, d = cc % nz;
+    const int Q = *nsrc_ptr;
+    int n = 0;
+    int out = FILL ? cnt_or_start[cc] : 0;
+    for (int q = 0; q < Q; ++q) {
+        int sc = src_cell[q];
+        int sa = sc / (ny * nz), sb = (sc / nz) % ny, sd = sc % nz;
+        bool nb = active && (abs(sa - a) <= 1) && (abs(sb - b) <= 1) && (abs(sd - d) <= 1);
+        if (nb) {
+            if (FILL) lists[out + n] = q;
+            n++;
+        }
+    }
+    if (!FILL && c <= ncell) cnt_or_start[c] = (c < ncell) ? n : 0;
+}
+
 constexpr int CT = 128;    // target sites per CTA
-constexpr int TILE = 256;  // sources per shared-memory tile
+constexpr int TILE = 128;  // sources per shared-memory tile
 
 // potential_solver_gpu.cu:1541-1562: V_i = sum_j v_solve(1e-10*|r_ij|, q_j), ascending j, overwrite.
-__global__ void __launch_bounds__(CT) coulomb_kernel(const double *__restrict__ x, const double *__restrict__ y,
-                                                    const double *__restrict__ z, const Source *__restrict__ src,
-                                                    const int *__restrict__ nsrc_ptr, double sigma, double k,
-                                                    double cutoff, int row_start, int row_count,
-                                                    double *__restrict__ pot) {
+// One CTA = up to CT targets of one cell; sources = that cell's neighbourhood list, tiled through shared memory.
+__global__ void __launch_bounds__(CT) coulomb_cell_kernel(const double *__restrict__ x, const double *__restrict__ y,
+                                                         const double *__restrict__ z, const Source *__restrict__ src,
+                                                         const int *__restrict__ blk_cell,
+                                                         const int *__restrict__ blk_start,
+                                                         const int *__restrict__ cell_tstart,
+                                                         const int *__restrict__ titems,
+                                                         const int *__restrict__ list_start,
+                                                         const int *__restrict__ lists, double sigma, double k,
+                                                         double cutoff, int row_start, int row_count,
+                                                         double *__restrict__ pot,
+                                                         unsigned long long *__restrict__ pair_counter) {
     __shared__ Source tile[TILE];
-    const int Q = *nsrc_ptr;
-    int idx = blockIdx.x * CT + threadIdx.x;
-    bool active = idx < row_count;
-    int i = row_start + (active ? idx : 0);
-    double xi = x[i], yi = y[i], zi = z[i];
+    const int c = blk_cell[blockIdx.x];
+    const int tpos = cell_tstart[c] + (blockIdx.x - blk_start[c]) * CT + threadIdx.x;
+    const bool in_cell = tpos < cell_tstart[c + 1];
+    const int i = in_cell ? titems[tpos] : -1;
+    const bool active = in_cell && i >= row_start && i < row_start + row_count;
+    double xi = 0, yi = 0, zi = 0;
+    if (active) { xi = x[i]; yi = y[i]; zi = z[i]; }
+    const int ls = list_start[c], le = list_start[c + 1];
     double local = 0.0;
-    for (int base = 0; base < Q; base += TILE) {
-        int nt = min(TILE, Q - base);
+    for (int base = ls; base < le; base += TILE) {
+        int nt = min(TILE, le - base);
         __syncthreads();
-        for (int t = threadIdx.x; t < nt; t += CT) tile[t] = src[base + t];
+        if (threadIdx.x < nt) tile[threadIdx.x] = src[lists[base + threadIdx.x]];
         __syncthreads();
         if (active) {
             for (int t = 0; t < nt; ++t) {
@@ -101,6 +174,7 @@ __global__ void __launch_bounds__(CT) coulomb_kernel(const double *__restrict__ 
         }
     }
     if (active) pot[i] = local;
+    if (threadIdx.x == 0 && pair_counter) atomicAdd(pair_counter, (unsigned long long)(le - ls) * CT);
 }
 
 __global__ void sum_kernel(double *__restrict__ a, const double *__restrict__ b, int n) {
@@ -125,42 +199,134 @@ extern "C" int kmcb200_update_charge(kmcb200_ctx *ctx, const int *element, int *
     return 0;
 }
 
+// Static plan for one (positions, N, cutoff): 20 A cell of every site, sites grouped by cell, CTA -> cell map.
+struct CoulombPlan {
+    const double *x = nullptr;
+    int N = 0;
+    double cutoff = 0;
+    unsigned long long checksum = 0;
+    CellGridDev g;
+    int ncell = 0, nblocks = 0;
+    int *site_cell = nullptr, *cell_tstart = nullptr, *titems = nullptr, *blk_start = nullptr, *blk_cell = nullptr;
+    int *list_start = nullptr;  // ncell+1 (per step)
+};
+static CoulombPlan g_plan[16];  // per device
+
+static int build_plan(kmcb200_ctx *ctx, CoulombPlan &P, int N, const double *x, const double *y, const double *z,
+                      double cutoff, unsigned long long checksum) {
+    if (P.x == x && P.N == N && P.cutoff == cutoff && P.checksum == checksum) return 0;
+    if (P.site_cell) {
+        KMC_CUDA(cudaStreamSynchronize(ctx->stream));
+        cudaFree(P.site_cell); cudaFree(P.cell_tstart); cudaFree(P.titems); cudaFree(P.blk_start); cudaFree(P.blk_cell);
+        cudaFree(P.list_start);
+        P = CoulombPlan();
+    }
+    CellGridDev g;
+    KMC_TRY(kmc_build_cellgrid(ctx, x, y, z, 0, N, cutoff, 0, nullptr, &g));  // scratch slots 0,1 hold start/items
+    int ncell = g.nx * g.ny * g.nz;
+    KMC_CUDA(cudaMalloc(&P.site_cell, (size_t)N * sizeof(int)));
+    KMC_CUDA(cudaMalloc(&P.cell_tstart, (size_t)(ncell + 1) * sizeof(int)));
+    KMC_CUDA(cudaMalloc(&P.titems, (size_t)N * sizeof(int)));
+    KMC_CUDA(cudaMalloc(&P.blk_start, (size_t)(ncell + 1) * sizeof(int)));
+    KMC_CUDA(cudaMalloc(&P.list_start, (size_t)(ncell + 1) * sizeof(int)));
+    KMC_CUDA(cudaMemcpyAsync(P.cell_tstart, g.cell_start, (size_t)(ncell + 1) * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+    KMC_CUDA(cudaMemcpyAsync(P.titems, g.items, (size_t)N * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+    kmc_count_launch();
+    site_cell_kernel<<<(N + 255) / 256, 256, 0, ctx->stream>>>(g, x, y, z, N, P.site_cell);
+    kmc_count_launch();
+    cell_blocks_kernel<<<(ncell + 1 + 255) / 256, 256, 0, ctx->stream>>>(P.cell_tstart, ncell, CT, P.blk_start);
+    KMC_CUDA(cudaGetLastError());
+    KMC_TRY(kmc_exclusive_scan_i32(ctx, P.blk_start, P.blk_start, (long long)ncell + 1, 4));
+    int nblocks = 0;
+    KMC_CUDA(cudaMemcpyAsync(&nblocks, P.blk_start + ncell, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    KMC_CUDA(cudaStreamSynchronize(ctx->stream));
+    KMC_CUDA(cudaMalloc(&P.blk_cell, (size_t)(nblocks + 1) * sizeof(int)));
+    kmc_count_launch();
+    block_map_kernel<<<(ncell + 255) / 256, 256, 0, ctx->stream>>>(P.blk_start, ncell, P.blk_cell);
+    KMC_CUDA(cudaGetLastError());
+    P.g = g;
+    P.g.cell_start = P.cell_tstart;
+    P.g.items = P.titems;
+    P.ncell = ncell;
+    P.nblocks = nblocks;
+    P.x = x; P.N = N; P.cutoff = cutoff; P.checksum = checksum;
+    return 0;
+}
+
 extern "C" int kmcb200_poisson_gridless(kmcb200_ctx *ctx, int N, const double *x, const double *y, const double *z,
                                         const int *element, const int *charge, double sigma, double k,
                                         double cutoff_radius, int row_start, int row_count,
                                         double *site_potential_charge) {
     KMC_CHECK_ARG(ctx && x && y && z && element && charge && site_potential_charge, "null pointer");
     KMC_CHECK_ARG(row_start >= 0 && row_count >= 0 && row_start + row_count <= N, "row range");
+    KMC_CHECK_ARG(ctx->device >= 0 && ctx->device < 16, "device ordinal");
     if (row_count == 0) return 0;
-    int *offs = nullptr;
+    CoulombPlan &P = g_plan[ctx->device];
+    // 1. charged sites, ascending site order (+ coordinate checksum for the cached plan)
+    int *offs = nullptr, *src_cell = nullptr, *lists = nullptr;
     Source *src = nullptr;
+    unsigned long long *csum = nullptr;
     KMC_TRY(kmc_scratch(ctx, 6, (size_t)(N + 1) * sizeof(int), (void **)&offs));
+    KMC_TRY(kmc_scratch(ctx, 10, 64, (void **)&csum));
+    KMC_CUDA(cudaMemsetAsync(csum, 0, 16, ctx->stream));
+    kmc_count_launch();
+    pos_checksum_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(x, y, z, N, csum + 1);
     kmc_count_launch();
     charged_flag_kernel<<<(N + 1 + 255) / 256, 256, 0, ctx->stream>>>(element, charge, N, offs);
     KMC_CUDA(cudaGetLastError());
     KMC_TRY(kmc_exclusive_scan_i32(ctx, offs, offs, (long long)N + 1, 4));  // offs[N] = Q
-    // capacity: worst case every site charged; the scratch buffer grows lazily to what was needed so far
-    int Q = 0;
     KMC_CUDA(cudaMemcpyAsync(ctx->h_mail, offs + N, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    KMC_CUDA(cudaMemcpyAsync((char *)ctx->h_mail + 8, csum + 1, 8, cudaMemcpyDeviceToHost, ctx->stream));
     KMC_CUDA(cudaStreamSynchronize(ctx->stream));
-    Q = *(int *)ctx->h_mail;
+    int Q = *(int *)ctx->h_mail;
+    unsigned long long checksum = *(unsigned long long *)((char *)ctx->h_mail + 8);
+    KMC_TRY(build_plan(ctx, P, N, x, y, z, cutoff_radius, checksum));
     KMC_TRY(kmc_scratch(ctx, 7, (size_t)(Q + 1) * sizeof(Source), (void **)&src));
+    KMC_TRY(kmc_scratch(ctx, 8, (size_t)(Q + 1) * sizeof(int), (void **)&src_cell));
     kmc_count_launch();
-    charged_scatter_kernel<<<(N + 255) / 256, 256, 0, ctx->stream>>>(charge, element, x, y, z, N, offs, src);
+    charged_scatter_kernel<<<(N + 255) / 256, 256, 0, ctx->stream>>>(charge, element, x, y, z, N, offs, P.site_cell, src,
+                                                                    src_cell);
     KMC_CUDA(cudaGetLastError());
+    // 2. per-cell neighbourhood source lists (count, scan, fill)
+    unsigned cb = (unsigned)((P.ncell + 1 + 127) / 128);
     kmc_count_launch();
-    coulomb_kernel<<<(row_count + CT - 1) / CT, CT, 0, ctx->stream>>>(x, y, z, src, offs + N, sigma, k, cutoff_radius,
-                                                                    row_start, row_count, site_potential_charge);
+    cell_sources_kernel<false><<<cb, 128, 0, ctx->stream>>>(P.g.nx, P.g.ny, P.g.nz, src_cell, offs + N, P.cell_tstart,
+                                                           P.list_start, nullptr);
     KMC_CUDA(cudaGetLastError());
+    KMC_TRY(kmc_exclusive_scan_i32(ctx, P.list_start, P.list_start, (long long)P.ncell + 1, 4));
+    KMC_CUDA(cudaMemcpyAsync(ctx->h_mail, P.list_start + P.ncell, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    KMC_CUDA(cudaStreamSynchronize(ctx->stream));
+    int total = *(int *)ctx->h_mail;
+    KMC_TRY(kmc_scratch(ctx, 9, (size_t)(total + 1) * sizeof(int), (void **)&lists));
+    kmc_count_launch();
+    cell_sources_kernel<true><<<cb, 128, 0, ctx->stream>>>(P.g.nx, P.g.ny, P.g.nz, src_cell, offs + N, P.cell_tstart,
+                                                          P.list_start, lists);
+    KMC_CUDA(cudaGetLastError());
+    // 3. the pair sum
+    unsigned long long *pairs = csum;  // csum[0] was zeroed above
+    if (P.nblocks > 0) {
+        kmc_count_launch();
+        coulomb_cell_kernel<<<P.nblocks, CT, 0, ctx->stream>>>(x, y, z, src, P.blk_cell, P.blk_start, P.cell_tstart,
+                                                              P.titems, P.list_start, lists, sigma, k, cutoff_radius,
+                                                              row_start, row_count, site_potential_charge, pairs);
+        KMC_CUDA(cudaGetLastError());
+    }
     ctx->last_num_charged = Q;
-    ctx->last_pair_tests = (long long)Q * row_count;
+    ctx->pair_counter_dev = pairs;
     return 0;
 }
 
 extern "C" int kmcb200_poisson_stats(kmcb200_ctx *ctx, long long *num_charged, long long *pair_tests) {
     KMC_CHECK_ARG(ctx != nullptr, "ctx");
     if (num_charged) *num_charged = ctx->last_num_charged;
-    if (pair_tests) *pair_tests = ctx->last_pair_tests;
+    if (pair_tests) {
+        *pair_tests = 0;
+        if (ctx->pair_counter_dev) {
+            KMC_CUDA(cudaMemcpyAsync(ctx->h_mail, ctx->pair_counter_dev, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+            KMC_CUDA(cudaStreamSynchronize(ctx->stream));
+            *pair_tests = (long long)*(unsigned long long *)ctx->h_mail;
+        }
+    }
     return 0;
 }
 

@@ -17,7 +17,7 @@
 #include "common.cuh"
 
 namespace {
-constexpr int EV_THREADS = 1024;
+constexpr int EV_THREADS = 512;
 constexpr int EV_GROUPS = EV_THREADS / 256;
 constexpr int MAX_DIRTY = 1024;
 constexpr int MAX_SUPER = 256;
@@ -144,10 +144,10 @@ __global__ void __launch_bounds__(256) build_rates_kernel(int N, int nn, const i
                                                          const int *__restrict__ charge, EvEnergies E,
                                                          double *__restrict__ prob, unsigned char *__restrict__ type,
                                                          double *__restrict__ rowsum, double *__restrict__ chunksum) {
-    __shared__ double rs[256];
     __shared__ double sm8[8];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int row0 = blockIdx.x * 256 + w * 32;
+    double my_rowsum = 0.0;  // lane q ends up holding the sum of row row0 + q
     for (int q = 0; q < 32; ++q) {
         int i = row0 + q;
         double s = 0.0;
@@ -183,13 +183,21 @@ __global__ void __launch_bounds__(256) build_rates_kernel(int N, int nn, const i
                     s = s + v;
                 }
             }
-            if (lane == 0) rowsum[i] = s;
         }
-        if (lane == 0) rs[w * 32 + q] = s;
+        if (lane == q) my_rowsum = s;
+    }
+    if (row0 + lane < N) rowsum[row0 + lane] = my_rowsum;
+    // block_scan_256 of the 256 row sums: this warp's Kogge-Stone part
+    double xs = kmc_warp_inclusive_scan(my_rowsum);
+    if (lane == 31) {
+        sm8[w] = xs;
     }
     __syncthreads();
-    double incl = block_scan_256_dev(rs[threadIdx.x], threadIdx.x, sm8);
-    if (threadIdx.x == 255) chunksum[blockIdx.x] = incl;
+    if (threadIdx.x == 0) {
+        double c = sm8[0];
+        for (int q = 1; q < 8; ++q) c = c + sm8[q];
+        chunksum[blockIdx.x] = c;  // == incl[255] of block_scan_256
+    }
 }
 
 __global__ void __launch_bounds__(256) super_sums_kernel(const double *__restrict__ chunksum, long long nchunk,
@@ -227,6 +235,12 @@ __device__ __forceinline__ double mt_next_double(unsigned *mt, int &pos) {
     return ret;
 }
 
+#ifdef KMC_EV_PROFILE
+#define EV_TICK(k) do { if (tid == 0) { long long now_ = clock64(); ph[k] += now_ - t_last; t_last = now_; } } while (0)
+#else
+#define EV_TICK(k) do { } while (0)
+#endif
+
 struct EvLoopArgs {
     int N, nn;
     long long nchunk, nsuper;
@@ -243,232 +257,354 @@ struct EvLoopArgs {
     double *log_psum;
     int log_cap;
     EvResult *result;
+    int chunks_in_smem;  // chunk sums cached in dynamic shared memory for the whole loop
+    long long *phase_cycles;  // 16 counters (KMC_EV_PROFILE builds)
 };
 
-// first t with incl > number, else last t with v > 0, else -1.  Group-parallel; result broadcast through smem.
-__device__ __forceinline__ void group_pick(double incl, double v, double number, int t, int *sm_first, int *sm_last) {
-    if (incl > number) atomicMin(sm_first, t);
-    if (v > 0.0) atomicMax(sm_last, t);
+// ---- block_scan_256 evaluated by ONE warp: lane l holds elements m*32 + l, m = 0..7 -------------------------
+// Identical association to block_scan_256_dev: Kogge-Stone per 32-element segment, sequential segment totals.
+struct Scan256 {
+    double incl[8];
+    double total;
+};
+__device__ __forceinline__ Scan256 warp_scan_256(const double v[8]) {
+    Scan256 r;
+    double x[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) x[m] = v[m];
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int d = 1; d <= 16; d <<= 1) {
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            double o = __shfl_up_sync(KMC_FULL_MASK, x[m], d);
+            if (lane >= d) x[m] = o + x[m];
+        }
+    }
+    double wc = __shfl_sync(KMC_FULL_MASK, x[0], 31);
+    r.incl[0] = x[0];
+#pragma unroll
+    for (int m = 1; m < 8; ++m) {
+        r.incl[m] = wc + x[m];
+        wc = wc + __shfl_sync(KMC_FULL_MASK, x[m], 31);
+    }
+    r.total = wc;
+    return r;
+}
+// first t (0..255) with incl[t] > number, else the last t with v[t] > 0, else -1; *prev = incl[t-1] (0 for t == 0)
+__device__ __forceinline__ int warp_pick_256(const Scan256 &sc, const double v[8], double number, double *prev) {
+    const int lane = threadIdx.x & 31;
+    int tsel = -1;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+        unsigned b = __ballot_sync(KMC_FULL_MASK, sc.incl[m] > number);
+        if (tsel < 0 && b) tsel = m * 32 + (__ffs(b) - 1);
+    }
+    if (tsel < 0) {
+#pragma unroll
+        for (int m = 7; m >= 0; --m) {
+            unsigned b = __ballot_sync(KMC_FULL_MASK, v[m] > 0.0);
+            if (tsel < 0 && b) tsel = m * 32 + (31 - __clz(b));
+        }
+    }
+    double pv = 0.0;
+    if (tsel > 0) {
+        int pm = (tsel - 1) >> 5, pl = (tsel - 1) & 31;
+        double cand = 0.0;
+#pragma unroll
+        for (int m = 0; m < 8; ++m)
+            if (m == pm) cand = sc.incl[m];
+        pv = __shfl_sync(KMC_FULL_MASK, cand, pl);
+    }
+    *prev = pv;
+    return tsel;
 }
 
+__device__ __forceinline__ bool smem_set_insert(int *table, int mask, int key) {
+    // open addressing; returns true if key was not present.  table entries are -1 when empty.
+    unsigned h = ((unsigned)key * 2654435761u) >> 7;
+    for (int probe = 0; probe <= mask; ++probe) {
+        int slot = (int)((h + probe) & (unsigned)mask);
+        int old = atomicCAS(table + slot, -1, key);
+        if (old == -1) return true;
+        if (old == key) return false;
+    }
+    return true;  // table full: treat as new (duplicates only cost redundant work)
+}
+
+// The persistent event loop: ONE CTA.  Warp 0 is the selector and runs the whole top-down search + event
+// application warp-synchronously (no block barrier); the repair of the partial sums is spread over all warps
+// (one warp per touched row / chunk / super).  Every phase issues all its global loads together, so a phase
+// costs about one L2/DRAM round trip.  5 block barriers per event.
 __global__ void __launch_bounds__(EV_THREADS, 1) event_loop_kernel(EvLoopArgs a) {
+    extern __shared__ double cs_smem[];  // chunk sums (when they fit)
     __shared__ unsigned mt[624];
-    __shared__ int mt_pos;
     __shared__ double ss[MAX_SUPER];
-    __shared__ double incl_sm[256];
-    __shared__ double sm8[EV_GROUPS][8];
-    __shared__ int dirty[MAX_DIRTY];
-    __shared__ int ndirty;
-    __shared__ unsigned char super_dirty[MAX_SUPER];
-    __shared__ int pick_first, pick_last;
-    __shared__ double s_number, s_psum, s_event_time;
-    __shared__ int s_sel, s_i, s_j, s_stop, s_nevents, s_error;
+    __shared__ int rows_list[MAX_DIRTY], chunk_list[MAX_DIRTY], super_list[MAX_SUPER];
+    __shared__ int row_set[2048], chunk_set[2048];
+    __shared__ unsigned char super_flag[MAX_SUPER];
+    __shared__ int n_rows, n_chunks, n_supers;
+    __shared__ double s_event_time;
+    __shared__ int s_i, s_j, s_stop, s_nevents, s_error, s_mtpos;
+    __shared__ int s_rev[4];
 
     const int tid = threadIdx.x;
-    const int grp = tid >> 8, t = tid & 255;
+    const int lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = EV_THREADS / 32;
     const int nn = a.nn;
+#ifdef KMC_EV_PROFILE
+    long long ph[16] = {0};
+    long long t_last = clock64();
+#endif
+    double *cs = a.chunks_in_smem ? cs_smem : a.chunksum;
+    if (a.chunks_in_smem)
+        for (long long q = tid; q < a.nchunk; q += EV_THREADS) cs_smem[q] = a.chunksum[q];
     for (int q = tid; q < 624; q += EV_THREADS) mt[q] = a.mt_state[q];
     for (int q = tid; q < MAX_SUPER; q += EV_THREADS) {
         ss[q] = (q < a.nsuper) ? a.supersum[q] : 0.0;
-        super_dirty[q] = 0;
+        super_flag[q] = 0;
     }
+    for (int q = tid; q < 2048; q += EV_THREADS) { row_set[q] = -1; chunk_set[q] = -1; }
     if (tid == 0) {
-        mt_pos = (int)a.mt_state[624];
+        s_mtpos = (int)a.mt_state[624];
         s_event_time = 0.0;
         s_nevents = 0;
         s_error = 0;
         s_stop = 0;
+        n_rows = 0; n_chunks = 0; n_supers = 0;
     }
     __syncthreads();
 
     while (true) {
-        // ---- loop condition (kmc_events.cu:448) + top level ---------------------------------------------
-        if (tid == 0) {
+        // =============================== selector: warp 0 ==============================================
+        if (warp == 0) {
+            int mt_pos = s_mtpos;
             bool go = (s_event_time < a.inv_freq_threshold) && (a.max_events <= 0 || s_nevents < a.max_events) && !s_error;
-            s_stop = !go;
+            int ei = -1, ej = -1;
             if (go) {
-                double acc = ss[0];
-                for (int s = 1; s < a.nsuper; ++s) acc = acc + ss[s];
-                double Psum = acc;
-                s_psum = Psum;
-                double number = mt_next_double(mt, mt_pos) * Psum;  // :469
-                int sel = -1;
-                if (Psum > 0.0) {
-                    double c = ss[0], prev = 0.0;
-                    for (int s = 0; s < a.nsuper; ++s) {
-                        if (s > 0) { prev = c; c = c + ss[s]; }
-                        if (c > number) { sel = s; if (s > 0) number = number - prev; break; }
+                // ---- top level: block_scan_256 over the super sums -----------------------------------------
+                double v[8];
+#pragma unroll
+                for (int m = 0; m < 8; ++m) v[m] = ss[m * 32 + lane];
+                Scan256 sc = warp_scan_256(v);
+                const double Psum = sc.total;
+                double u1 = 0.0;
+                if (lane == 0) u1 = mt_next_double(mt, mt_pos);  // kmc_events.cu:469
+                u1 = __shfl_sync(KMC_FULL_MASK, u1, 0);
+                double number = u1 * Psum;
+                double prev;
+                int ts = (Psum > 0.0) ? warp_pick_256(sc, v, number, &prev) : -1;
+                long long r = -1;
+                if (ts >= 0) {
+                    number = number - prev;
+                    // ---- chunk level ----------------------------------------------------------------------
+#pragma unroll
+                    for (int m = 0; m < 8; ++m) {
+                        long long c = (long long)ts * 256 + m * 32 + lane;
+                        v[m] = (c < a.nchunk) ? cs[c] : 0.0;
                     }
-                    if (sel < 0) {  // rounding pushed number past the total: clamp to the last non-empty super
-                        double c2 = ss[0];
-                        double prev2 = 0.0;
-                        int last = -1; double last_prev = 0.0;
-                        for (int s = 0; s < a.nsuper; ++s) {
-                            if (s > 0) { prev2 = c2; c2 = c2 + ss[s]; }
-                            if (ss[s] > 0.0) { last = s; last_prev = prev2; }
+                    sc = warp_scan_256(v);
+                    int tc = warp_pick_256(sc, v, number, &prev);
+                    if (tc >= 0) {
+                        number = number - prev;
+                        const long long chunk = (long long)ts * 256 + tc;
+                        // ---- row level ----------------------------------------------------------------------
+#pragma unroll
+                        for (int m = 0; m < 8; ++m) {
+                            long long rr = chunk * 256 + m * 32 + lane;
+                            v[m] = (rr < a.N) ? a.rowsum[rr] : 0.0;
                         }
-                        sel = last;
-                        if (sel > 0) number = number - last_prev;
+                        sc = warp_scan_256(v);
+                        int tr = warp_pick_256(sc, v, number, &prev);
+                        if (tr >= 0) {
+                            number = number - prev;
+                            r = chunk * 256 + tr;
+                        }
                     }
                 }
-                s_sel = sel;
-                s_number = number;
-                pick_first = 256;
-                pick_last = -1;
+                if (r >= 0) {
+                    // ---- slot level: lanes hold slots lane and lane+32; walk the non-zero slots in order --------
+                    const long long base = r * (long long)nn;
+                    double p0 = 0.0, p1 = 0.0;
+                    int nb0 = -1, nb1 = -1, ty0 = KMCB200_NULL_EVENT, ty1 = KMCB200_NULL_EVENT;
+                    if (lane < nn) { p0 = a.prob[base + lane]; nb0 = a.neigh[base + lane]; ty0 = a.type[base + lane]; }
+                    if (lane + 32 < nn) { p1 = a.prob[base + lane + 32]; nb1 = a.neigh[base + lane + 32]; ty1 = a.type[base + lane + 32]; }
+                    int rp = 0;
+                    if (lane < 2) rp = a.rev_ptr[r + lane];
+                    unsigned m0 = __ballot_sync(KMC_FULL_MASK, p0 > 0.0), m1 = __ballot_sync(KMC_FULL_MASK, p1 > 0.0);
+                    int seln = -1, lastn = -1;
+                    double acc = 0.0;
+                    bool first = true;
+                    // adding an exact zero never changes acc, so only non-zero slots can make acc exceed number
+                    unsigned long long mm = ((unsigned long long)m1 << 32) | m0;
+                    while (mm) {
+                        int n = __ffsll((long long)mm) - 1;
+                        mm &= mm - 1;
+                        double pv = __shfl_sync(KMC_FULL_MASK, (n < 32) ? p0 : p1, n & 31);
+                        acc = first ? (0.0 + pv) : (acc + pv);
+                        first = false;
+                        lastn = n;
+                        if (acc > number) { seln = n; break; }
+                    }
+                    if (seln < 0) seln = lastn;
+                    if (seln >= 0) {
+                        const int j = __shfl_sync(KMC_FULL_MASK, (seln < 32) ? nb0 : nb1, seln & 31);
+                        const int ty = __shfl_sync(KMC_FULL_MASK, (seln < 32) ? ty0 : ty1, seln & 31);
+                        const int i = (int)r;
+                        int rj = 0;
+                        if (lane >= 2 && lane < 4) rj = a.rev_ptr[j + lane - 2];
+                        if (lane == 0) {
+                            int ne = s_nevents;
+                            if (ne < a.log_cap) {
+                                a.log[4 * ne + 0] = i; a.log[4 * ne + 1] = j; a.log[4 * ne + 2] = ty;
+                                a.log[4 * ne + 3] = (int)(base + seln);
+                                a.log_psum[ne] = Psum;
+                            }
+                            // execute_event: kmc_events.cu:305-328
+                            if (ty == KMCB200_VACANCY_GENERATION) {
+                                a.element[i] = KMCB200_OXYGEN_DEFECT; a.element[j] = KMCB200_VACANCY;
+                                a.charge[i] = -2; a.charge[j] = 2;
+                            } else if (ty == KMCB200_VACANCY_RECOMBINATION) {
+                                a.element[i] = KMCB200_DEFECT; a.element[j] = KMCB200_O;
+                                a.charge[i] = 0; a.charge[j] = 0;
+                            } else if (ty == KMCB200_VACANCY_DIFFUSION || ty == KMCB200_ION_DIFFUSION) {
+                                int e_i = a.element[i], e_j = a.element[j], q_i = a.charge[i], q_j = a.charge[j];
+                                a.element[i] = e_j; a.element[j] = e_i;
+                                a.charge[i] = q_j; a.charge[j] = q_i;
+                            }
+                        }
+                        if (lane < 2) s_rev[lane] = rp;
+                        if (lane >= 2 && lane < 4) s_rev[lane] = rj;
+                        ei = i;
+                        ej = j;
+                    }
+                }
+                // ---- residence time (kmc_events.cu:515) ----------------------------------------------------
+                if (lane == 0) {
+                    double u2 = mt_next_double(mt, mt_pos);
+                    s_event_time = -log(u2) / Psum;
+                    s_nevents = s_nevents + 1;
+                    s_mtpos = mt_pos;
+                }
+            }
+            if (lane == 0) {
+                s_stop = !go;
+                s_i = ei;
+                s_j = ej;
+                if (ei >= 0) {
+                    rows_list[0] = ei;
+                    rows_list[1] = ej;
+                    n_rows = 2;
+                } else {
+                    n_rows = 0;
+                }
             }
         }
         __syncthreads();
+        EV_TICK(0);
         if (s_stop) break;
-        int sel_super = s_sel;
-        if (sel_super >= 0) {
-            // ---- chunk level (all groups compute redundantly; group 0 publishes) ---------------------------
-            long long c_idx = (long long)sel_super * 256 + t;
-            double v = (c_idx < a.nchunk) ? a.chunksum[c_idx] : 0.0;
-            double incl = block_scan_256_dev(v, t, sm8[grp]);
-            if (grp == 0) { incl_sm[t] = incl; group_pick(incl, v, s_number, t, &pick_first, &pick_last); }
-            __syncthreads();
-            if (tid == 0) {
-                int tc = (pick_first < 256) ? pick_first : pick_last;
-                if (tc > 0) s_number = s_number - incl_sm[tc - 1];
-                s_sel = tc;
-                pick_first = 256;
-                pick_last = -1;
+        const int ei = s_i, ej = s_j;
+        if (ei >= 0) {
+            // ---- zero-out (zero_out_events_split, kmc_events.cu:247-266) through the reverse index.  Padded slots
+            // already hold rate 0 / NULL_EVENT, so rows ei and ej are cleared entirely.
+            if (tid < 2 * nn) {
+                long long sl = (long long)((tid < nn) ? ei : ej) * nn + (tid < nn ? tid : tid - nn);
+                a.prob[sl] = 0.0;
+                a.type[sl] = KMCB200_NULL_EVENT;
             }
-            __syncthreads();
-            int tc = s_sel;
-            long long chunk = (long long)sel_super * 256 + tc;
-            // ---- row level --------------------------------------------------------------------------------
-            long long r_idx = chunk * 256 + t;
-            v = (tc >= 0 && r_idx < a.N) ? a.rowsum[r_idx] : 0.0;
-            incl = block_scan_256_dev(v, t, sm8[grp]);
-            if (grp == 0) { incl_sm[t] = incl; group_pick(incl, v, s_number, t, &pick_first, &pick_last); }
-            __syncthreads();
-            // ---- slot level + apply (thread 0) --------------------------------------------------------------
-            if (tid == 0) {
-                int tr = (tc >= 0) ? ((pick_first < 256) ? pick_first : pick_last) : -1;
-                long long slot = -1;
-                if (tr >= 0) {
-                    double number = s_number;
-                    if (tr > 0) number = number - incl_sm[tr - 1];
-                    long long r = chunk * 256 + tr;
-                    const double *p = a.prob + r * (long long)nn;
-                    double acc = p[0];
-                    int seln = -1;
-                    for (int n = 0; n < nn; ++n) {
-                        if (n > 0) acc = acc + p[n];
-                        if (acc > number) { seln = n; break; }
-                    }
-                    if (seln < 0)
-                        for (int n = nn - 1; n >= 0; --n)
-                            if (p[n] > 0.0) { seln = n; break; }
-                    if (seln >= 0) slot = r * (long long)nn + seln;
-                }
-                s_i = -1;
-                s_j = -1;
-                if (slot >= 0) {
-                    int i = (int)(slot / nn);
-                    int j = a.neigh[slot];
-                    int ty = a.type[slot];
-                    int ne = s_nevents;
-                    if (ne < a.log_cap) {
-                        a.log[4 * ne + 0] = i; a.log[4 * ne + 1] = j; a.log[4 * ne + 2] = ty; a.log[4 * ne + 3] = (int)slot;
-                        a.log_psum[ne] = s_psum;
-                    }
-                    // execute_event: kmc_events.cu:305-328
-                    if (ty == KMCB200_VACANCY_GENERATION) {
-                        a.element[i] = KMCB200_OXYGEN_DEFECT; a.element[j] = KMCB200_VACANCY;
-                        a.charge[i] = -2; a.charge[j] = 2;
-                    } else if (ty == KMCB200_VACANCY_RECOMBINATION) {
-                        a.element[i] = KMCB200_DEFECT; a.element[j] = KMCB200_O;
-                        a.charge[i] = 0; a.charge[j] = 0;
-                    } else if (ty == KMCB200_VACANCY_DIFFUSION || ty == KMCB200_ION_DIFFUSION) {
-                        int te = a.element[i]; a.element[i] = a.element[j]; a.element[j] = te;
-                        int tq = a.charge[i]; a.charge[i] = a.charge[j]; a.charge[j] = tq;
-                    }
-                    s_i = i;
-                    s_j = j;
-                    dirty[0] = i;
-                    dirty[1] = j;
-                    ndirty = 2;
-                } else {
-                    ndirty = 0;
-                }
-            }
-            __syncthreads();
-            const int ei = s_i, ej = s_j;
-            if (ei >= 0) {
-                // ---- zero-out (zero_out_events_split, kmc_events.cu:247-266) through the reverse index -------
-                for (int q = tid; q < 2 * nn; q += EV_THREADS) {
-                    long long sl = (long long)((q < nn) ? ei : ej) * nn + (q % nn);
-                    if (a.neigh[sl] >= 0) { a.prob[sl] = 0.0; a.type[sl] = KMCB200_NULL_EVENT; }
-                }
-                for (int which = 0; which < 2; ++which) {
-                    int s = which ? ej : ei;
-                    int b = a.rev_ptr[s], e = a.rev_ptr[s + 1];
-                    for (int q = b + tid; q < e; q += EV_THREADS) {
-                        int sl = a.rev_slot[q];
-                        a.prob[sl] = 0.0;
-                        a.type[sl] = KMCB200_NULL_EVENT;
-                        int pos = atomicAdd(&ndirty, 1);
-                        if (pos < MAX_DIRTY) dirty[pos] = sl / nn;
+            {
+                const int b0 = s_rev[0], n0 = s_rev[1] - b0, b1 = s_rev[2], n1 = s_rev[3] - b1;
+                for (int q = tid; q < n0 + n1; q += EV_THREADS) {
+                    int sl = (q < n0) ? a.rev_slot[b0 + q] : a.rev_slot[b1 + (q - n0)];
+                    a.prob[sl] = 0.0;
+                    a.type[sl] = KMCB200_NULL_EVENT;
+                    int rr = sl / nn;
+                    if (rr != ei && rr != ej && smem_set_insert(row_set, 2047, rr)) {
+                        int pos = atomicAdd(&n_rows, 1);
+                        if (pos < MAX_DIRTY) rows_list[pos] = rr;
                         else s_error = 1;
                     }
                 }
-                __syncthreads();
-                int nd = min(ndirty, MAX_DIRTY);
-                // ---- repair row sums ---------------------------------------------------------------------
-                for (int q = tid; q < nd; q += EV_THREADS) {
-                    int r = dirty[q];
-                    const double *p = a.prob + (long long)r * nn;
-                    double s = p[0];
-                    for (int n = 1; n < nn; ++n) s = s + p[n];
-                    a.rowsum[r] = s;
-                    super_dirty[r >> 16] = 1;
-                }
-                __syncthreads();
-                // ---- repair chunk sums: EV_GROUPS chunks per round ------------------------------------------
-                for (int base = 0; base < nd; base += EV_GROUPS) {
-                    int q = base + grp;
-                    long long c = -1;
-                    if (q < nd) {
-                        c = dirty[q] >> 8;
-                        if (q > 0 && (dirty[q - 1] >> 8) == c) c = -1;  // same chunk as the previous entry
-                    }
-                    long long r_i = c * 256 + t;
-                    double vv = (c >= 0 && r_i < a.N) ? a.rowsum[r_i] : 0.0;
-                    double inc = block_scan_256_dev(vv, t, sm8[grp]);
-                    if (c >= 0 && t == 255) a.chunksum[c] = inc;
-                }
-                __syncthreads();
-                // ---- repair super sums ---------------------------------------------------------------------
-                for (int s = 0; s < a.nsuper; ++s) {
-                    if (super_dirty[s]) {  // uniform (shared memory)
-                        long long c_i = (long long)s * 256 + t;
-                        double vv = (c_i < a.nchunk) ? a.chunksum[c_i] : 0.0;
-                        double inc = block_scan_256_dev(vv, t, sm8[grp]);
-                        if (tid == 255) { ss[s] = inc; a.supersum[s] = inc; }
-                        __syncthreads();
-                        if (tid == 0) super_dirty[s] = 0;
-                    }
-                }
-                __syncthreads();
             }
+            __syncthreads();
+            EV_TICK(1);
+            const int nd = min(n_rows, MAX_DIRTY);
+            // ---- repair row sums: one warp per touched row; sequential sum == sum over its non-zero slots in order
+            for (int q = warp; q < nd; q += NW) {
+                const int rr = rows_list[q];
+                double s = 0.0;
+                if (q >= 2) {
+                    const long long base = (long long)rr * nn;
+                    double p0 = (lane < nn) ? a.prob[base + lane] : 0.0;
+                    double p1 = (lane + 32 < nn) ? a.prob[base + lane + 32] : 0.0;
+                    unsigned m0 = __ballot_sync(KMC_FULL_MASK, p0 != 0.0), m1 = __ballot_sync(KMC_FULL_MASK, p1 != 0.0);
+                    unsigned long long mm = ((unsigned long long)m1 << 32) | m0;
+                    while (mm) {
+                        int n = __ffsll((long long)mm) - 1;
+                        mm &= mm - 1;
+                        s = s + __shfl_sync(KMC_FULL_MASK, (n < 32) ? p0 : p1, n & 31);
+                    }
+                }
+                if (lane == 0) {
+                    a.rowsum[rr] = s;
+                    if (smem_set_insert(chunk_set, 2047, rr >> 8)) chunk_list[atomicAdd(&n_chunks, 1)] = rr >> 8;
+                }
+            }
+            __syncthreads();
+            EV_TICK(2);
+            // ---- repair chunk sums: one warp per touched chunk (block_scan_256 of its 256 row sums) -----------------
+            const int nc = n_chunks;
+            for (int q = warp; q < nc; q += NW) {
+                const int c = chunk_list[q];
+                double v[8];
+#pragma unroll
+                for (int m = 0; m < 8; ++m) {
+                    long long rr = (long long)c * 256 + m * 32 + lane;
+                    v[m] = (rr < a.N) ? a.rowsum[rr] : 0.0;
+                }
+                Scan256 sc = warp_scan_256(v);
+                if (lane == 0) {
+                    cs[c] = sc.total;
+                    if (a.chunks_in_smem) a.chunksum[c] = sc.total;
+                    super_flag[c >> 8] = 1;
+                }
+            }
+            __syncthreads();
+            EV_TICK(3);
+            // ---- repair super sums: one warp per touched super ------------------------------------------------------
+            for (int s = warp; s < (int)a.nsuper; s += NW) {
+                if (super_flag[s]) {
+                    double v[8];
+#pragma unroll
+                    for (int m = 0; m < 8; ++m) {
+                        long long c = (long long)s * 256 + m * 32 + lane;
+                        v[m] = (c < a.nchunk) ? cs[c] : 0.0;
+                    }
+                    Scan256 sc = warp_scan_256(v);
+                    if (lane == 0) {
+                        ss[s] = sc.total;
+                        a.supersum[s] = sc.total;
+                        super_flag[s] = 0;
+                    }
+                }
+            }
+            // reset the de-duplication sets
+            for (int q = tid; q < 2048; q += EV_THREADS) { row_set[q] = -1; chunk_set[q] = -1; }
+            if (tid == 0) { n_chunks = 0; }
+            __syncthreads();
+            EV_TICK(4);
         }
-        // ---- residence time (kmc_events.cu:515) -----------------------------------------------------------
-        if (tid == 0) {
-            double u2 = mt_next_double(mt, mt_pos);
-            s_event_time = -log(u2) / s_psum;
-            s_nevents = s_nevents + 1;
-        }
-        __syncthreads();
     }
     for (int q = tid; q < 624; q += EV_THREADS) a.mt_state[q] = mt[q];
     if (tid == 0) {
-        a.mt_state[624] = (unsigned)mt_pos;
+        a.mt_state[624] = (unsigned)s_mtpos;
         a.result->event_time = s_event_time;
-        a.result->psum_last = s_psum;
+        a.result->psum_last = 0.0;
         a.result->n_events = s_nevents;
         a.result->error = s_error;
+#ifdef KMC_EV_PROFILE
+        if (a.phase_cycles) for (int q = 0; q < 16; ++q) a.phase_cycles[q] = ph[q];
+#endif
     }
 }
 
@@ -646,8 +782,20 @@ extern "C" int kmcb200_execute_kmc_step(kmcb200_ctx *ctx, kmcb200_events *ev, in
     a.max_events = max_events;
     a.log = ev->log; a.log_psum = ev->log_psum; a.log_cap = ev->log_cap;
     a.result = ev->result;
+    a.phase_cycles = nullptr;
+#ifdef KMC_EV_PROFILE
+    KMC_TRY(kmc_scratch(ctx, 5, 16 * sizeof(long long), (void **)&a.phase_cycles));
+#endif
+    size_t dyn = (size_t)ev->nchunk * sizeof(double);
+    a.chunks_in_smem = dyn <= 160 * 1024 ? 1 : 0;  // up to ~5.2 M sites; larger devices read chunk sums from L2
+    if (!a.chunks_in_smem) dyn = 0;
+    static size_t configured = 0;
+    if (dyn > configured) {
+        KMC_CUDA(cudaFuncSetAttribute(event_loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(160 * 1024)));
+        configured = 160 * 1024;
+    }
     kmc_count_launch();
-    event_loop_kernel<<<1, EV_THREADS, 0, ctx->stream>>>(a);
+    event_loop_kernel<<<1, EV_THREADS, dyn, ctx->stream>>>(a);
     KMC_CUDA(cudaGetLastError());
     EvResult *h = (EvResult *)ctx->h_mail;
     KMC_CUDA(cudaMemcpyAsync(h, ev->result, sizeof(EvResult), cudaMemcpyDeviceToHost, ctx->stream));
@@ -656,6 +804,15 @@ extern "C" int kmcb200_execute_kmc_step(kmcb200_ctx *ctx, kmcb200_events *ev, in
         kmc_set_error("event loop: more than %d touched rows in one event", MAX_DIRTY);
         return KMCB200_E_CAPACITY;
     }
+#ifdef KMC_EV_PROFILE
+    {
+        long long ph[16];
+        cudaMemcpy(ph, a.phase_cycles, sizeof(ph), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[ev profile] events=%d cycles/event:", h->n_events);
+        for (int q = 0; q < 5; ++q) fprintf(stderr, " p%d=%.0f", q, (double)ph[q] / (h->n_events > 0 ? h->n_events : 1));
+        fprintf(stderr, "\n");
+    }
+#endif
     ev->last_n_events = h->n_events;
     if (event_time_host) *event_time_host = h->event_time;
     if (n_events_host) *n_events_host = h->n_events;

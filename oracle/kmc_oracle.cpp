@@ -14,6 +14,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <random>
 #include <sstream>
@@ -265,15 +266,18 @@ struct EventSums {
         block_scan_256(v, incl);
         supersum[s] = incl[255];
     }
+    // top level: one more block_scan_256 over the (<= 256) super sums; topcum = its inclusive prefixes
     void recompute_top() {
-        double acc = supersum[0];
-        topcum[0] = acc;
-        for (long s = 1; s < nsuper; ++s) { acc = acc + supersum[s]; topcum[s] = acc; }
+        double v[256];
+        for (int t = 0; t < 256; ++t) v[t] = (t < nsuper) ? supersum[t] : 0.0;
+        topcum.resize(256);
+        block_scan_256(v, topcum.data());
     }
     void build(int N_, int nn_, const double *prob) {
         N = N_; nn = nn_;
         nchunk = (N + 255) / 256;
         nsuper = (nchunk + 255) / 256;
+        if (nsuper > 256) { std::fprintf(stderr, "oracle: event hierarchy supports <= 16.7M sites\n"); std::abort(); }
         rowsum.resize(N); chunksum.resize(nchunk); supersum.resize(nsuper); topcum.resize(nsuper);
 #pragma omp parallel for schedule(static)
         for (long r = 0; r < N; ++r) rowsum[r] = row_sum(prob, r);
@@ -282,7 +286,7 @@ struct EventSums {
         for (long s = 0; s < nsuper; ++s) recompute_super(s);
         recompute_top();
     }
-    double psum() const { return topcum[nsuper - 1]; }
+    double psum() const { return topcum[255]; }
 
     // first index t in incl[0..255] with incl[t] > number, else last t with v[t] > 0 (clamp)
     static int pick(const double *v, const double *incl, double number) {
@@ -294,10 +298,9 @@ struct EventSums {
     }
     long select(const double *prob, double number) const {
         if (!(psum() > 0.0)) return -1;
-        long s = -1;
-        for (long q = 0; q < nsuper; ++q)
-            if (topcum[q] > number) { s = q; break; }
-        if (s < 0) for (long q = nsuper - 1; q >= 0; --q) if (supersum[q] > 0.0) { s = q; break; }
+        double tv[256];
+        for (int t = 0; t < 256; ++t) tv[t] = (t < nsuper) ? supersum[t] : 0.0;
+        long s = pick(tv, topcum.data(), number);
         if (s < 0) return -1;
         if (s > 0) number = number - topcum[s - 1];
         double v[256], incl[256];
