@@ -7,22 +7,27 @@ NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 --fmad=false -std=c++17 -diag-suppress 549 -Xcompiler -fPIC -Xcompiler -O2 -ccbin /usr/bin/g++ ${KMC_NVCC_EXTRA}"
 mkdir -p "$HERE/build"
 objs=""
+pids=""
 for f in ctx scan lists kmat pcg coulomb events comm; do
   src="$HERE/csrc/$f.cu"
   [ -f "$src" ] || continue
   obj="$HERE/build/$f.o"
   if [ ! -f "$obj" ] || [ "$src" -nt "$obj" ] || [ -n "$(find "$HERE/csrc" "$HERE/../include" -newer "$obj" \( -name '*.cuh' -o -name '*.h' \) | head -1)" ]; then
     echo "nvcc $f.cu"
+    rm -f "$obj"
     $NVCC $FLAGS -c "$src" -o "$obj" &
+    pids="$pids $!"
   fi
   objs="$objs $obj"
 done
 obj="$HERE/build/host_model.o"
 if [ ! -f "$obj" ] || [ "$HERE/host/host_model.cpp" -nt "$obj" ] || [ "$HERE/../include/kmc_b200.h" -nt "$obj" ]; then
   echo "g++ host_model.cpp"
+  rm -f "$obj"
   /usr/bin/g++ -O2 -std=c++17 -ffp-contract=off -fPIC -c "$HERE/host/host_model.cpp" -o "$obj" &
+  pids="$pids $!"
 fi
 objs="$objs $obj"
-wait
+for p in $pids; do wait $p || { echo "build.sh: compilation failed" >&2; exit 1; }; done
 $NVCC -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT" $objs -cudart static -ccbin /usr/bin/g++
 echo "built $OUT"

@@ -40,7 +40,7 @@ struct kmcb200_events {
     long long nchunk = 0, nsuper = 0;
     double *prob = nullptr;
     unsigned char *type = nullptr;
-    double *rowsum = nullptr, *chunksum = nullptr, *supersum = nullptr;
+    double *rowsum = nullptr, *gtot = nullptr, *chunksum = nullptr, *supersum = nullptr;  // gtot: per 8 rows
     int *rev_ptr = nullptr, *rev_slot = nullptr;
     unsigned *mt = nullptr;  // 624 words + pos
     int *log = nullptr;
@@ -68,21 +68,70 @@ __global__ void rev_fill_kernel(const int *__restrict__ neigh, long long total, 
     if (j >= 0) rev_slot[rev_ptr[j] + atomicAdd(fill + j, 1)] = (int)s;
 }
 
-// summation spec block_scan_256 for one 256-thread group; every thread of the CTA must call it.
-__device__ __forceinline__ double block_scan_256_dev(double v, int t, double *sm8) {
-    double x = kmc_warp_inclusive_scan(v);
-    int w = t >> 5;
-    if ((t & 31) == 31) sm8[w] = x;
-    __syncthreads();
-    double incl = x;
-    if (w > 0) {
-        double pre = sm8[0];
-        for (int q = 1; q < w; ++q) pre = pre + sm8[q];
-        incl = pre + x;
+// ---- summation spec scan_256, evaluated by ONE warp: lane l owns the 8 consecutive elements 8l..8l+7 ----------
+// a[k] = sequential prefix inside the lane; lane totals are Kogge-Stone scanned across the warp;
+// incl[8l+k] = S[l-1] + a[k]; group total = S[31].
+struct Scan256 {
+    double a[8];   // in: values, out: lane-local inclusive prefixes
+    double excl;   // S[l-1] (unused for lane 0)
+    double total;  // S[31]
+};
+__device__ __forceinline__ void warp_scan_256(Scan256 &r) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 1; k < 8; ++k) r.a[k] = r.a[k - 1] + r.a[k];
+    double S = r.a[7];
+#pragma unroll
+    for (int d = 1; d <= 16; d <<= 1) {
+        double o = __shfl_up_sync(KMC_FULL_MASK, S, d);
+        if (lane >= d) S = o + S;
     }
-    __syncthreads();
-    return incl;
+    r.excl = __shfl_up_sync(KMC_FULL_MASK, S, 1);
+    r.total = __shfl_sync(KMC_FULL_MASK, S, 31);
 }
+__device__ __forceinline__ double scan_incl(const Scan256 &r, int k) {
+    return ((threadIdx.x & 31) > 0) ? (r.excl + r.a[k]) : r.a[k];
+}
+// first t (0..255) with incl[t] > number, else the last t with v[t] > 0, else -1; *prev = incl[t-1] (0 for t == 0).
+// v: the original values (before the scan).
+__device__ __forceinline__ int warp_pick_256(const Scan256 &sc, const double v[8], double number, double *prev) {
+    const int lane = threadIdx.x & 31;
+    double inc[8];
+    int kfirst = 8, klast = -1;
+#pragma unroll
+    for (int k = 7; k >= 0; --k) {
+        inc[k] = scan_incl(sc, k);
+        if (inc[k] > number) kfirst = k;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        if (v[k] > 0.0) klast = k;
+    int tsel = -1;
+    unsigned bf = __ballot_sync(KMC_FULL_MASK, kfirst < 8);
+    if (bf) {
+        int l = __ffs(bf) - 1;
+        tsel = l * 8 + __shfl_sync(KMC_FULL_MASK, kfirst, l);
+    } else {
+        unsigned bl = __ballot_sync(KMC_FULL_MASK, klast >= 0);
+        if (bl) {
+            int l = 31 - __clz(bl);
+            tsel = l * 8 + __shfl_sync(KMC_FULL_MASK, klast, l);
+        }
+    }
+    double pv = 0.0;
+    if (tsel > 0) {
+        int pl = (tsel - 1) >> 3, pk = (tsel - 1) & 7;
+        double cand = inc[0];
+#pragma unroll
+        for (int k = 1; k < 8; ++k)
+            if (k == pk) cand = inc[k];
+        pv = __shfl_sync(KMC_FULL_MASK, cand, pl);
+    }
+    *prev = pv;
+    return tsel;
+}
+// butterfly row sum of the summation spec: lane l holds p[l] + p[l+32]
+__device__ __forceinline__ double warp_row_sum(double p0, double p1) { return kmc_warp_xor_sum(p0 + p1); }
 
 // rate of one (i, slot) pair: kmc_events.cu:141-228
 __device__ __forceinline__ double event_rate(int i, int j, int el_i, int c_i, double pot_i, double xi, double yi,
@@ -143,8 +192,9 @@ __global__ void __launch_bounds__(256) build_rates_kernel(int N, int nn, const i
                                                          const int *__restrict__ element,
                                                          const int *__restrict__ charge, EvEnergies E,
                                                          double *__restrict__ prob, unsigned char *__restrict__ type,
-                                                         double *__restrict__ rowsum, double *__restrict__ chunksum) {
-    __shared__ double sm8[8];
+                                                         double *__restrict__ rowsum, double *__restrict__ gtot,
+                                                         double *__restrict__ chunksum) {
+    __shared__ double rs[256];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int row0 = blockIdx.x * 256 + w * 32;
     double my_rowsum = 0.0;  // lane q ends up holding the sum of row row0 + q
@@ -175,38 +225,37 @@ __global__ void __launch_bounds__(256) build_rates_kernel(int N, int nn, const i
             }
             if (lane < nn) { prob[base + lane] = P0; type[base + lane] = (unsigned char)e0; }
             if (lane + 32 < nn) { prob[base + lane + 32] = P1; type[base + lane + 32] = (unsigned char)e1; }
-            // row sum: sequential over the nn slots (summation spec); all-zero rows short-cut to +0.0
-            if (__any_sync(KMC_FULL_MASK, (P0 != 0.0) || (P1 != 0.0))) {
-                s = __shfl_sync(KMC_FULL_MASK, P0, 0);
-                for (int n = 1; n < nn; ++n) {
-                    double v = __shfl_sync(KMC_FULL_MASK, (n < 32) ? P0 : P1, n & 31);
-                    s = s + v;
-                }
-            }
+            // row sum (summation spec): butterfly over the lanes; all-zero rows short-cut to +0.0
+            if (__any_sync(KMC_FULL_MASK, (P0 != 0.0) || (P1 != 0.0))) s = warp_row_sum(P0, P1);
         }
         if (lane == q) my_rowsum = s;
     }
     if (row0 + lane < N) rowsum[row0 + lane] = my_rowsum;
-    // block_scan_256 of the 256 row sums: this warp's Kogge-Stone part
-    double xs = kmc_warp_inclusive_scan(my_rowsum);
-    if (lane == 31) {
-        sm8[w] = xs;
-    }
+    rs[w * 32 + lane] = my_rowsum;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        double c = sm8[0];
-        for (int q = 1; q < 8; ++q) c = c + sm8[q];
-        chunksum[blockIdx.x] = c;  // == incl[255] of block_scan_256
+    // scan_256 of the 256 row sums by warp 0: group-of-8 totals are kept (gtot) for the incremental repair
+    if (w == 0) {
+        Scan256 sc;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sc.a[k] = rs[8 * lane + k];
+        warp_scan_256(sc);
+        gtot[(size_t)blockIdx.x * 32 + lane] = sc.a[7];
+        if (lane == 0) chunksum[blockIdx.x] = sc.total;
     }
 }
 
-__global__ void __launch_bounds__(256) super_sums_kernel(const double *__restrict__ chunksum, long long nchunk,
-                                                        double *__restrict__ supersum) {
-    __shared__ double sm8[8];
-    long long c = (long long)blockIdx.x * 256 + threadIdx.x;
-    double v = (c < nchunk) ? chunksum[c] : 0.0;
-    double incl = block_scan_256_dev(v, threadIdx.x, sm8);
-    if (threadIdx.x == 255) supersum[blockIdx.x] = incl;
+// one warp per super: scan_256 total of its 256 chunk sums
+__global__ void __launch_bounds__(32) super_sums_kernel(const double *__restrict__ chunksum, long long nchunk,
+                                                       double *__restrict__ supersum) {
+    const int lane = threadIdx.x;
+    Scan256 sc;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        long long c = (long long)blockIdx.x * 256 + 8 * lane + k;
+        sc.a[k] = (c < nchunk) ? chunksum[c] : 0.0;
+    }
+    warp_scan_256(sc);
+    if (lane == 0) supersum[blockIdx.x] = sc.total;
 }
 
 // ---- MT19937 (std::mt19937) + libstdc++ generate_canonical<double,53> -----------------------------------
@@ -247,7 +296,7 @@ struct EvLoopArgs {
     const int *neigh;
     double *prob;
     unsigned char *type;
-    double *rowsum, *chunksum, *supersum;
+    double *rowsum, *gtot, *chunksum, *supersum;
     const int *rev_ptr, *rev_slot;
     int *element, *charge;
     unsigned *mt_state;  // 624 + pos
@@ -260,65 +309,6 @@ struct EvLoopArgs {
     int chunks_in_smem;  // chunk sums cached in dynamic shared memory for the whole loop
     long long *phase_cycles;  // 16 counters (KMC_EV_PROFILE builds)
 };
-
-// ---- block_scan_256 evaluated by ONE warp: lane l holds elements m*32 + l, m = 0..7 -------------------------
-// Identical association to block_scan_256_dev: Kogge-Stone per 32-element segment, sequential segment totals.
-struct Scan256 {
-    double incl[8];
-    double total;
-};
-__device__ __forceinline__ Scan256 warp_scan_256(const double v[8]) {
-    Scan256 r;
-    double x[8];
-#pragma unroll
-    for (int m = 0; m < 8; ++m) x[m] = v[m];
-    const int lane = threadIdx.x & 31;
-#pragma unroll
-    for (int d = 1; d <= 16; d <<= 1) {
-#pragma unroll
-        for (int m = 0; m < 8; ++m) {
-            double o = __shfl_up_sync(KMC_FULL_MASK, x[m], d);
-            if (lane >= d) x[m] = o + x[m];
-        }
-    }
-    double wc = __shfl_sync(KMC_FULL_MASK, x[0], 31);
-    r.incl[0] = x[0];
-#pragma unroll
-    for (int m = 1; m < 8; ++m) {
-        r.incl[m] = wc + x[m];
-        wc = wc + __shfl_sync(KMC_FULL_MASK, x[m], 31);
-    }
-    r.total = wc;
-    return r;
-}
-// first t (0..255) with incl[t] > number, else the last t with v[t] > 0, else -1; *prev = incl[t-1] (0 for t == 0)
-__device__ __forceinline__ int warp_pick_256(const Scan256 &sc, const double v[8], double number, double *prev) {
-    const int lane = threadIdx.x & 31;
-    int tsel = -1;
-#pragma unroll
-    for (int m = 0; m < 8; ++m) {
-        unsigned b = __ballot_sync(KMC_FULL_MASK, sc.incl[m] > number);
-        if (tsel < 0 && b) tsel = m * 32 + (__ffs(b) - 1);
-    }
-    if (tsel < 0) {
-#pragma unroll
-        for (int m = 7; m >= 0; --m) {
-            unsigned b = __ballot_sync(KMC_FULL_MASK, v[m] > 0.0);
-            if (tsel < 0 && b) tsel = m * 32 + (31 - __clz(b));
-        }
-    }
-    double pv = 0.0;
-    if (tsel > 0) {
-        int pm = (tsel - 1) >> 5, pl = (tsel - 1) & 31;
-        double cand = 0.0;
-#pragma unroll
-        for (int m = 0; m < 8; ++m)
-            if (m == pm) cand = sc.incl[m];
-        pv = __shfl_sync(KMC_FULL_MASK, cand, pl);
-    }
-    *prev = pv;
-    return tsel;
-}
 
 __device__ __forceinline__ bool smem_set_insert(int *table, int mask, int key) {
     // open addressing; returns true if key was not present.  table entries are -1 when empty.
@@ -382,12 +372,14 @@ __global__ void __launch_bounds__(EV_THREADS, 1) event_loop_kernel(EvLoopArgs a)
             bool go = (s_event_time < a.inv_freq_threshold) && (a.max_events <= 0 || s_nevents < a.max_events) && !s_error;
             int ei = -1, ej = -1;
             if (go) {
-                // ---- top level: block_scan_256 over the super sums -----------------------------------------
+                // ---- top level: scan_256 over the super sums (shared memory) ------------------------------
+                Scan256 sc;
                 double v[8];
 #pragma unroll
-                for (int m = 0; m < 8; ++m) v[m] = ss[m * 32 + lane];
-                Scan256 sc = warp_scan_256(v);
+                for (int k = 0; k < 8; ++k) { v[k] = ss[8 * lane + k]; sc.a[k] = v[k]; }
+                warp_scan_256(sc);
                 const double Psum = sc.total;
+                EV_TICK(8);
                 double u1 = 0.0;
                 if (lane == 0) u1 = mt_next_double(mt, mt_pos);  // kmc_events.cu:469
                 u1 = __shfl_sync(KMC_FULL_MASK, u1, 0);
@@ -399,23 +391,35 @@ __global__ void __launch_bounds__(EV_THREADS, 1) event_loop_kernel(EvLoopArgs a)
                     number = number - prev;
                     // ---- chunk level ----------------------------------------------------------------------
 #pragma unroll
-                    for (int m = 0; m < 8; ++m) {
-                        long long c = (long long)ts * 256 + m * 32 + lane;
-                        v[m] = (c < a.nchunk) ? cs[c] : 0.0;
+                    for (int k = 0; k < 8; ++k) {
+                        long long c = (long long)ts * 256 + 8 * lane + k;
+                        v[k] = (c < a.nchunk) ? cs[c] : 0.0;
+                        sc.a[k] = v[k];
                     }
-                    sc = warp_scan_256(v);
+                    warp_scan_256(sc);
                     int tc = warp_pick_256(sc, v, number, &prev);
+                    EV_TICK(9);
                     if (tc >= 0) {
                         number = number - prev;
                         const long long chunk = (long long)ts * 256 + tc;
                         // ---- row level ----------------------------------------------------------------------
+                        const long long rbase = chunk * 256 + 8 * lane;
+                        if (rbase + 8 <= a.N) {
+                            const double2 *src2 = reinterpret_cast<const double2 *>(a.rowsum + rbase);
 #pragma unroll
-                        for (int m = 0; m < 8; ++m) {
-                            long long rr = chunk * 256 + m * 32 + lane;
-                            v[m] = (rr < a.N) ? a.rowsum[rr] : 0.0;
+                            for (int k = 0; k < 4; ++k) {
+                                double2 t2 = src2[k];
+                                v[2 * k] = t2.x; v[2 * k + 1] = t2.y;
+                            }
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) v[k] = (rbase + k < a.N) ? a.rowsum[rbase + k] : 0.0;
                         }
-                        sc = warp_scan_256(v);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) sc.a[k] = v[k];
+                        warp_scan_256(sc);
                         int tr = warp_pick_256(sc, v, number, &prev);
+                        EV_TICK(10);
                         if (tr >= 0) {
                             number = number - prev;
                             r = chunk * 256 + tr;
@@ -447,6 +451,7 @@ __global__ void __launch_bounds__(EV_THREADS, 1) event_loop_kernel(EvLoopArgs a)
                         if (acc > number) { seln = n; break; }
                     }
                     if (seln < 0) seln = lastn;
+                    EV_TICK(11);
                     if (seln >= 0) {
                         const int j = __shfl_sync(KMC_FULL_MASK, (seln < 32) ? nb0 : nb1, seln & 31);
                         const int ty = __shfl_sync(KMC_FULL_MASK, (seln < 32) ? ty0 : ty1, seln & 31);
@@ -479,6 +484,7 @@ __global__ void __launch_bounds__(EV_THREADS, 1) event_loop_kernel(EvLoopArgs a)
                         ej = j;
                     }
                 }
+                EV_TICK(12);
                 // ---- residence time (kmc_events.cu:515) ----------------------------------------------------
                 if (lane == 0) {
                     double u2 = mt_next_double(mt, mt_pos);
@@ -529,62 +535,103 @@ __global__ void __launch_bounds__(EV_THREADS, 1) event_loop_kernel(EvLoopArgs a)
             __syncthreads();
             EV_TICK(1);
             const int nd = min(n_rows, MAX_DIRTY);
-            // ---- repair row sums: one warp per touched row; sequential sum == sum over its non-zero slots in order
-            for (int q = warp; q < nd; q += NW) {
-                const int rr = rows_list[q];
-                double s = 0.0;
-                if (q >= 2) {
-                    const long long base = (long long)rr * nn;
-                    double p0 = (lane < nn) ? a.prob[base + lane] : 0.0;
-                    double p1 = (lane + 32 < nn) ? a.prob[base + lane + 32] : 0.0;
-                    unsigned m0 = __ballot_sync(KMC_FULL_MASK, p0 != 0.0), m1 = __ballot_sync(KMC_FULL_MASK, p1 != 0.0);
-                    unsigned long long mm = ((unsigned long long)m1 << 32) | m0;
-                    while (mm) {
-                        int n = __ffsll((long long)mm) - 1;
-                        mm &= mm - 1;
-                        s = s + __shfl_sync(KMC_FULL_MASK, (n < 32) ? p0 : p1, n & 31);
+#ifdef KMC_EV_PROFILE
+            if (tid == 0) ph[14] += nd;
+#endif
+            // ---- repair row sums: one warp per touched row, 4 rows in flight per warp (butterfly row sum) ------------
+            for (int base = 2; base < nd; base += NW * 4) {
+                double p0[4], p1[4];
+                int rr[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    int q = base + u * NW + warp;
+                    rr[u] = (q < nd) ? rows_list[q] : -1;
+                    p0[u] = 0.0; p1[u] = 0.0;
+                    if (rr[u] >= 0) {
+                        const long long b = (long long)rr[u] * nn;
+                        if (lane < nn) p0[u] = a.prob[b + lane];
+                        if (lane + 32 < nn) p1[u] = a.prob[b + lane + 32];
                     }
                 }
-                if (lane == 0) {
-                    a.rowsum[rr] = s;
-                    if (smem_set_insert(chunk_set, 2047, rr >> 8)) chunk_list[atomicAdd(&n_chunks, 1)] = rr >> 8;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (rr[u] < 0) continue;
+                    double sacc = warp_row_sum(p0[u], p1[u]);
+                    if (lane == 0) {
+                        a.rowsum[rr[u]] = sacc;
+                        if (smem_set_insert(chunk_set, 2047, rr[u] >> 3)) chunk_list[atomicAdd(&n_chunks, 1)] = rr[u] >> 3;
+                    }
                 }
+            }
+            if (tid < 2) {  // rows ei / ej are entirely zero now
+                int r2 = rows_list[tid];
+                a.rowsum[r2] = 0.0;
+                if (smem_set_insert(chunk_set, 2047, r2 >> 3)) chunk_list[atomicAdd(&n_chunks, 1)] = r2 >> 3;
             }
             __syncthreads();
             EV_TICK(2);
-            // ---- repair chunk sums: one warp per touched chunk (block_scan_256 of its 256 row sums) -----------------
-            const int nc = n_chunks;
-            for (int q = warp; q < nc; q += NW) {
-                const int c = chunk_list[q];
-                double v[8];
+            // ---- repair the group-of-8 totals (sequential part of scan_256): one thread per touched group ------------
+            const int ngrp_d = n_chunks;  // chunk_list holds unique GROUP ids (row >> 3) here
+#ifdef KMC_EV_PROFILE
+            if (tid == 0) ph[15] += ngrp_d;
+#endif
+            for (int q = tid; q < ngrp_d; q += EV_THREADS) {
+                const int g = chunk_list[q];
+                const long long rb = (long long)g * 8;
+                double w[8];
+                if (rb + 8 <= a.N) {
+                    const double2 *src2 = reinterpret_cast<const double2 *>(a.rowsum + rb);
 #pragma unroll
-                for (int m = 0; m < 8; ++m) {
-                    long long rr = (long long)c * 256 + m * 32 + lane;
-                    v[m] = (rr < a.N) ? a.rowsum[rr] : 0.0;
+                    for (int m = 0; m < 4; ++m) { double2 t2 = src2[m]; w[2 * m] = t2.x; w[2 * m + 1] = t2.y; }
+                } else {
+#pragma unroll
+                    for (int m = 0; m < 8; ++m) w[m] = (rb + m < a.N) ? a.rowsum[rb + m] : 0.0;
                 }
-                Scan256 sc = warp_scan_256(v);
-                if (lane == 0) {
-                    cs[c] = sc.total;
-                    if (a.chunks_in_smem) a.chunksum[c] = sc.total;
-                    super_flag[c >> 8] = 1;
+                double acc = w[0];
+#pragma unroll
+                for (int m = 1; m < 8; ++m) acc = acc + w[m];
+                a.gtot[g] = acc;
+            }
+            __syncthreads();
+            EV_TICK(5);
+            // ---- chunk sums: Kogge-Stone over the 32 group totals of the chunk; one warp per touched group's chunk
+            // (duplicate chunks write the same value), 4 in flight
+            for (int base = 0; base < ngrp_d; base += NW * 4) {
+                double tv[4];
+                int cc[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    int q = base + u * NW + warp;
+                    cc[u] = (q < ngrp_d) ? (chunk_list[q] >> 5) : -1;
+                    tv[u] = (cc[u] >= 0) ? a.gtot[(long long)cc[u] * 32 + lane] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (cc[u] < 0) continue;
+                    double S = kmc_warp_inclusive_scan(tv[u]);
+                    if (lane == 31) {
+                        cs[cc[u]] = S;
+                        if (a.chunks_in_smem) a.chunksum[cc[u]] = S;
+                        super_flag[cc[u] >> 8] = 1;
+                    }
                 }
             }
             __syncthreads();
             EV_TICK(3);
             // ---- repair super sums: one warp per touched super ------------------------------------------------------
-            for (int s = warp; s < (int)a.nsuper; s += NW) {
-                if (super_flag[s]) {
-                    double v[8];
+            for (int sidx = warp; sidx < (int)a.nsuper; sidx += NW) {
+                if (super_flag[sidx]) {
+                    Scan256 sc;
 #pragma unroll
-                    for (int m = 0; m < 8; ++m) {
-                        long long c = (long long)s * 256 + m * 32 + lane;
-                        v[m] = (c < a.nchunk) ? cs[c] : 0.0;
+                    for (int k = 0; k < 8; ++k) {
+                        long long c = (long long)sidx * 256 + 8 * lane + k;
+                        sc.a[k] = (c < a.nchunk) ? cs[c] : 0.0;
                     }
-                    Scan256 sc = warp_scan_256(v);
+                    warp_scan_256(sc);
                     if (lane == 0) {
-                        ss[s] = sc.total;
-                        a.supersum[s] = sc.total;
-                        super_flag[s] = 0;
+                        ss[sidx] = sc.total;
+                        a.supersum[sidx] = sc.total;
+                        super_flag[sidx] = 0;
                     }
                 }
             }
@@ -638,6 +685,7 @@ extern "C" int kmcb200_events_create(kmcb200_ctx *ctx, int N, int nn, const int 
     A((void **)&ev->prob, (size_t)total * sizeof(double));
     A((void **)&ev->type, (size_t)total);
     A((void **)&ev->rowsum, (size_t)N * sizeof(double));
+    A((void **)&ev->gtot, (size_t)(ev->nchunk * 32) * sizeof(double));
     A((void **)&ev->chunksum, (size_t)ev->nchunk * sizeof(double));
     A((void **)&ev->supersum, (size_t)MAX_SUPER * sizeof(double));
     A((void **)&ev->rev_ptr, (size_t)(N + 1) * sizeof(int));
@@ -678,7 +726,7 @@ extern "C" int kmcb200_events_create(kmcb200_ctx *ctx, int N, int nn, const int 
 extern "C" int kmcb200_events_destroy(kmcb200_events *ev) {
     if (!ev) return 0;
     if (ev->ctx) cudaStreamSynchronize(ev->ctx->stream);
-    cudaFree(ev->prob); cudaFree(ev->type); cudaFree(ev->rowsum); cudaFree(ev->chunksum); cudaFree(ev->supersum);
+    cudaFree(ev->prob); cudaFree(ev->type); cudaFree(ev->rowsum); cudaFree(ev->gtot); cudaFree(ev->chunksum); cudaFree(ev->supersum);
     cudaFree(ev->rev_ptr); cudaFree(ev->rev_slot); cudaFree(ev->mt); cudaFree(ev->log); cudaFree(ev->log_psum);
     cudaFree(ev->result);
     delete ev;
@@ -756,10 +804,10 @@ extern "C" int kmcb200_build_event_list(kmcb200_ctx *ctx, kmcb200_events *ev, in
     build_rates_kernel<<<(unsigned)ev->nchunk, 256, 0, ctx->stream>>>(N, nn, neigh, site_layer, kT, freq, sigma, k, x, y,
                                                                      z, site_potential_charge, site_element,
                                                                      site_charge, ev->energies, ev->prob, ev->type,
-                                                                     ev->rowsum, ev->chunksum);
+                                                                     ev->rowsum, ev->gtot, ev->chunksum);
     KMC_CUDA(cudaGetLastError());
     kmc_count_launch();
-    super_sums_kernel<<<(unsigned)ev->nsuper, 256, 0, ctx->stream>>>(ev->chunksum, ev->nchunk, ev->supersum);
+    super_sums_kernel<<<(unsigned)ev->nsuper, 32, 0, ctx->stream>>>(ev->chunksum, ev->nchunk, ev->supersum);
     KMC_CUDA(cudaGetLastError());
     return 0;
 }
@@ -783,6 +831,7 @@ extern "C" int kmcb200_execute_kmc_step(kmcb200_ctx *ctx, kmcb200_events *ev, in
     a.log = ev->log; a.log_psum = ev->log_psum; a.log_cap = ev->log_cap;
     a.result = ev->result;
     a.phase_cycles = nullptr;
+    a.gtot = ev->gtot;
 #ifdef KMC_EV_PROFILE
     KMC_TRY(kmc_scratch(ctx, 5, 16 * sizeof(long long), (void **)&a.phase_cycles));
 #endif
@@ -809,7 +858,7 @@ extern "C" int kmcb200_execute_kmc_step(kmcb200_ctx *ctx, kmcb200_events *ev, in
         long long ph[16];
         cudaMemcpy(ph, a.phase_cycles, sizeof(ph), cudaMemcpyDeviceToHost);
         fprintf(stderr, "[ev profile] events=%d cycles/event:", h->n_events);
-        for (int q = 0; q < 5; ++q) fprintf(stderr, " p%d=%.0f", q, (double)ph[q] / (h->n_events > 0 ? h->n_events : 1));
+        for (int q = 0; q < 16; ++q) fprintf(stderr, " p%d=%.0f", q, (double)ph[q] / (h->n_events > 0 ? h->n_events : 1));
         fprintf(stderr, "\n");
     }
 #endif

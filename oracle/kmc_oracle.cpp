@@ -209,38 +209,44 @@ void spmv_spec(long n, const int *row_ptr, const int *col, const double *data, c
 }
 
 // ---- hierarchical event sums -------------------------------------
-// Inclusive scan of 256 values exactly as the CUDA block scan: Kogge-Stone inside each warp
-// (d = 1,2,4,8,16: if lane >= d: x += x[lane-d]), sequential scan of the 8 warp totals, then
-// incl[t] = warp_prefix[w-1] + x[t].
-void block_scan_256(const double *v, double *incl) {
-    double x[256], nx[256];
-    for (int t = 0; t < 256; ++t) x[t] = v[t];
+// scan_256: inclusive scan of 256 values as ONE warp computes it on the GPU.  Lane l (0..31) owns the 8
+// consecutive elements 8l..8l+7 and sums them sequentially (a[l][k]); the 32 lane totals are scanned with
+// Kogge-Stone (d = 1,2,4,8,16: if lane >= d: S += S[lane-d]); incl[8l+k] = S[l-1] + a[l][k] (a[0][k] for l = 0).
+// Returns the group total S[31] (the Kogge-Stone value; it may differ from incl[255] in the last bit).
+double scan_256(const double *v, double *incl) {
+    double a[32][8], S[32], nS[32];
+    for (int l = 0; l < 32; ++l) {
+        a[l][0] = v[8 * l];
+        for (int k = 1; k < 8; ++k) a[l][k] = a[l][k - 1] + v[8 * l + k];
+        S[l] = a[l][7];
+    }
     for (int d = 1; d <= 16; d <<= 1) {
-        for (int t = 0; t < 256; ++t) {
-            int l = t & 31;
-            nx[t] = (l >= d) ? (x[t - d] + x[t]) : x[t];
-        }
-        for (int t = 0; t < 256; ++t) x[t] = nx[t];
+        for (int l = 0; l < 32; ++l) nS[l] = (l >= d) ? (S[l - d] + S[l]) : S[l];
+        for (int l = 0; l < 32; ++l) S[l] = nS[l];
     }
-    double wc[8];
-    wc[0] = x[31];
-    for (int w = 1; w < 8; ++w) wc[w] = wc[w - 1] + x[32 * w + 31];
-    for (int t = 0; t < 256; ++t) {
-        int w = t >> 5;
-        incl[t] = (w > 0) ? (wc[w - 1] + x[t]) : x[t];
-    }
+    if (incl)
+        for (int l = 0; l < 32; ++l)
+            for (int k = 0; k < 8; ++k) incl[8 * l + k] = (l > 0) ? (S[l - 1] + a[l][k]) : a[l][k];
+    return S[31];
 }
+void block_scan_256(const double *v, double *incl) { scan_256(v, incl); }
 
 struct EventSums {
     int N, nn;
     long nchunk, nsuper;
     std::vector<double> rowsum, chunksum, supersum, topcum;
+    double total = 0.0;
 
+    // row sum: lane l holds p[l] + p[l+32] (0 beyond nn), then the 32-lane butterfly (xor 16,8,4,2,1)
     inline double row_sum(const double *prob, long r) const {
         const double *p = prob + r * (long)nn;
-        double s = p[0];
-        for (int n = 1; n < nn; ++n) s = s + p[n];
-        return s;
+        double v[32];
+        for (int l = 0; l < 32; ++l) {
+            double p0 = (l < nn) ? p[l] : 0.0;
+            double p1 = (l + 32 < nn) ? p[l + 32] : 0.0;
+            v[l] = p0 + p1;
+        }
+        return warp_xor_reduce32(v);
     }
     void chunk_vals(long c, double *v) const {
         for (int t = 0; t < 256; ++t) {
@@ -255,23 +261,21 @@ struct EventSums {
         }
     }
     void recompute_chunk(long c) {
-        double v[256], incl[256];
+        double v[256];
         chunk_vals(c, v);
-        block_scan_256(v, incl);
-        chunksum[c] = incl[255];
+        chunksum[c] = scan_256(v, nullptr);
     }
     void recompute_super(long s) {
-        double v[256], incl[256];
+        double v[256];
         super_vals(s, v);
-        block_scan_256(v, incl);
-        supersum[s] = incl[255];
+        supersum[s] = scan_256(v, nullptr);
     }
     // top level: one more block_scan_256 over the (<= 256) super sums; topcum = its inclusive prefixes
     void recompute_top() {
         double v[256];
         for (int t = 0; t < 256; ++t) v[t] = (t < nsuper) ? supersum[t] : 0.0;
         topcum.resize(256);
-        block_scan_256(v, topcum.data());
+        total = scan_256(v, topcum.data());
     }
     void build(int N_, int nn_, const double *prob) {
         N = N_; nn = nn_;
@@ -286,7 +290,7 @@ struct EventSums {
         for (long s = 0; s < nsuper; ++s) recompute_super(s);
         recompute_top();
     }
-    double psum() const { return topcum[255]; }
+    double psum() const { return total; }
 
     // first index t in incl[0..255] with incl[t] > number, else last t with v[t] > 0 (clamp)
     static int pick(const double *v, const double *incl, double number) {
