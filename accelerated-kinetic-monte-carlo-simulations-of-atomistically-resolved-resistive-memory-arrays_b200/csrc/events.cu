@@ -40,8 +40,8 @@ struct kmcb200_events {
     long long nchunk = 0, nsuper = 0;
     double *prob = nullptr;
     unsigned char *type = nullptr;
-    double *rowsum = nullptr, *gtot = nullptr, *chunksum = nullptr, *supersum = nullptr;  // gtot: per 8 rows
-    int *rev_ptr = nullptr, *rev_slot = nullptr;
+    double *rowsum = nullptr, *chunksum = nullptr, *supersum = nullptr;
+    int *rev = nullptr;  // N * REV_STRIDE
     unsigned *mt = nullptr;  // 624 words + pos
     int *log = nullptr;
     double *log_psum = nullptr;
@@ -54,18 +54,18 @@ struct kmcb200_events {
 
 namespace {
 
-__global__ void rev_count_kernel(const int *__restrict__ neigh, long long total, int *__restrict__ cnt) {
+constexpr int REV_STRIDE = 64;  // max number of rows that list a given site (in-degree of the neighbour graph)
+// reverse neighbour index, fixed stride: rev[s*64 + q] = slot (r*nn + n) with neigh[r][n] == s, -1 padded
+__global__ void rev_fill_kernel(const int *__restrict__ neigh, long long total, int *__restrict__ fill,
+                                int *__restrict__ rev, int *__restrict__ overflow) {
     long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= total) return;
     int j = neigh[s];
-    if (j >= 0) atomicAdd(cnt + j, 1);
-}
-__global__ void rev_fill_kernel(const int *__restrict__ neigh, long long total, const int *__restrict__ rev_ptr,
-                                int *__restrict__ fill, int *__restrict__ rev_slot) {
-    long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= total) return;
-    int j = neigh[s];
-    if (j >= 0) rev_slot[rev_ptr[j] + atomicAdd(fill + j, 1)] = (int)s;
+    if (j >= 0) {
+        int pos = atomicAdd(fill + j, 1);
+        if (pos < REV_STRIDE - 1) rev[(size_t)j * REV_STRIDE + pos] = (int)s;  // last entry stays free (-1)
+        else atomicExch(overflow, 1);
+    }
 }
 
 // ---- summation spec scan_256, evaluated by ONE warp: lane l owns the 8 consecutive elements 8l..8l+7 ----------
@@ -192,8 +192,7 @@ __global__ void __launch_bounds__(256) build_rates_kernel(int N, int nn, const i
                                                          const int *__restrict__ element,
                                                          const int *__restrict__ charge, EvEnergies E,
                                                          double *__restrict__ prob, unsigned char *__restrict__ type,
-                                                         double *__restrict__ rowsum, double *__restrict__ gtot,
-                                                         double *__restrict__ chunksum) {
+                                                         double *__restrict__ rowsum, double *__restrict__ chunksum) {
     __shared__ double rs[256];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int row0 = blockIdx.x * 256 + w * 32;
@@ -233,13 +232,12 @@ __global__ void __launch_bounds__(256) build_rates_kernel(int N, int nn, const i
     if (row0 + lane < N) rowsum[row0 + lane] = my_rowsum;
     rs[w * 32 + lane] = my_rowsum;
     __syncthreads();
-    // scan_256 of the 256 row sums by warp 0: group-of-8 totals are kept (gtot) for the incremental repair
+    // scan_256 of the 256 row sums by warp 0
     if (w == 0) {
         Scan256 sc;
 #pragma unroll
         for (int k = 0; k < 8; ++k) sc.a[k] = rs[8 * lane + k];
         warp_scan_256(sc);
-        gtot[(size_t)blockIdx.x * 32 + lane] = sc.a[7];
         if (lane == 0) chunksum[blockIdx.x] = sc.total;
     }
 }
@@ -296,8 +294,8 @@ struct EvLoopArgs {
     const int *neigh;
     double *prob;
     unsigned char *type;
-    double *rowsum, *gtot, *chunksum, *supersum;
-    const int *rev_ptr, *rev_slot;
+    double *rowsum, *chunksum, *supersum;
+    const int *rev;
     int *element, *charge;
     unsigned *mt_state;  // 624 + pos
     double inv_freq_threshold;  // 1/freq
@@ -322,21 +320,43 @@ __device__ __forceinline__ bool smem_set_insert(int *table, int mask, int key) {
     return true;  // table full: treat as new (duplicates only cost redundant work)
 }
 
-// The persistent event loop: ONE CTA.  Warp 0 is the selector and runs the whole top-down search + event
-// application warp-synchronously (no block barrier); the repair of the partial sums is spread over all warps
-// (one warp per touched row / chunk / super).  Every phase issues all its global loads together, so a phase
-// costs about one L2/DRAM round trip.  5 block barriers per event.
+// Draws the (u1, u2) pair of one event ahead of time.  Remembers how to undo it (position + pre-twist state), because
+// the pair drawn for the event that ends the loop is never consumed and the generator must stay in step with the host's.
+__device__ __forceinline__ void rng_prefetch_pair(unsigned *mt, unsigned *mt_backup, int *mtpos, int *pos_before,
+                                                  int *backup_valid, double *pair) {
+    int pos = *mtpos;
+    *pos_before = pos;
+    if (pos + 4 > 624) {
+        for (int q = 0; q < 624; ++q) mt_backup[q] = mt[q];
+        *backup_valid = 1;
+    } else {
+        *backup_valid = 0;
+    }
+    pair[0] = mt_next_double(mt, pos);
+    pair[1] = mt_next_double(mt, pos);
+    *mtpos = pos;
+}
+
+// The persistent event loop: ONE CTA.  Every phase issues all its global loads together, so a phase costs about
+// one L2/DRAM round trip; 4 block barriers per event:
+//   S  warp 0 (selector, warp-synchronous): top -> chunk -> row (1 RT) -> slot (1 RT); publishes (i, j, type)
+//   Z  all warps: zero-out through the fixed-stride reverse index (1 RT) + list of touched rows / unique chunks;
+//      one spare thread applies the event to element/charge, another draws the residence time
+//   R  one warp per touched chunk: new sums of its touched rows + scan_256 of the chunk's 256 row sums (1 RT)
+//   U  one warp per touched super: scan_256 of its chunk sums (shared memory)
 __global__ void __launch_bounds__(EV_THREADS, 1) event_loop_kernel(EvLoopArgs a) {
     extern __shared__ double cs_smem[];  // chunk sums (when they fit)
     __shared__ unsigned mt[624];
     __shared__ double ss[MAX_SUPER];
     __shared__ int rows_list[MAX_DIRTY], chunk_list[MAX_DIRTY], super_list[MAX_SUPER];
-    __shared__ int row_set[2048], chunk_set[2048];
-    __shared__ unsigned char super_flag[MAX_SUPER];
+    __shared__ int chunk_set[1024];
+    __shared__ int super_flag[MAX_SUPER];
     __shared__ int n_rows, n_chunks, n_supers;
-    __shared__ double s_event_time;
-    __shared__ int s_i, s_j, s_stop, s_nevents, s_error, s_mtpos;
-    __shared__ int s_rev[4];
+    __shared__ double s_event_time, s_u2, s_psum;
+    __shared__ double s_upair[2][2];  // uniforms of event e live in s_upair[e & 1] (drawn one event ahead by warp 1)
+    __shared__ unsigned mt_backup[624];
+    __shared__ int s_pos_before, s_backup_valid;
+    __shared__ int s_i, s_j, s_ty, s_slot, s_stop, s_nevents, s_error, s_mtpos;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -354,7 +374,7 @@ __global__ void __launch_bounds__(EV_THREADS, 1) event_loop_kernel(EvLoopArgs a)
         ss[q] = (q < a.nsuper) ? a.supersum[q] : 0.0;
         super_flag[q] = 0;
     }
-    for (int q = tid; q < 2048; q += EV_THREADS) { row_set[q] = -1; chunk_set[q] = -1; }
+    for (int q = tid; q < 1024; q += EV_THREADS) chunk_set[q] = -1;
     if (tid == 0) {
         s_mtpos = (int)a.mt_state[624];
         s_event_time = 0.0;
@@ -364,13 +384,18 @@ __global__ void __launch_bounds__(EV_THREADS, 1) event_loop_kernel(EvLoopArgs a)
         n_rows = 0; n_chunks = 0; n_supers = 0;
     }
     __syncthreads();
+    if (tid == 32) rng_prefetch_pair(mt, mt_backup, &s_mtpos, &s_pos_before, &s_backup_valid, s_upair[0]);
+    __syncthreads();
 
     while (true) {
-        // =============================== selector: warp 0 ==============================================
+        // =============================== S: selector, warp 0 ===========================================
+        if (warp == 1 && lane == 0) {  // draw the uniforms of the NEXT event while warp 0 selects the current one
+            bool go1 = (s_event_time < a.inv_freq_threshold) && (a.max_events <= 0 || s_nevents < a.max_events) && !s_error;
+            if (go1) rng_prefetch_pair(mt, mt_backup, &s_mtpos, &s_pos_before, &s_backup_valid, s_upair[(s_nevents + 1) & 1]);
+        }
         if (warp == 0) {
-            int mt_pos = s_mtpos;
             bool go = (s_event_time < a.inv_freq_threshold) && (a.max_events <= 0 || s_nevents < a.max_events) && !s_error;
-            int ei = -1, ej = -1;
+            int ei = -1, ej = -1, ety = KMCB200_NULL_EVENT, eslot = -1;
             if (go) {
                 // ---- top level: scan_256 over the super sums (shared memory) ------------------------------
                 Scan256 sc;
@@ -379,13 +404,17 @@ __global__ void __launch_bounds__(EV_THREADS, 1) event_loop_kernel(EvLoopArgs a)
                 for (int k = 0; k < 8; ++k) { v[k] = ss[8 * lane + k]; sc.a[k] = v[k]; }
                 warp_scan_256(sc);
                 const double Psum = sc.total;
-                EV_TICK(8);
-                double u1 = 0.0;
-                if (lane == 0) u1 = mt_next_double(mt, mt_pos);  // kmc_events.cu:469
-                u1 = __shfl_sync(KMC_FULL_MASK, u1, 0);
+                // u1 (selection, kmc_events.cu:469) and u2 (residence time, :515) were drawn by warp 1 during the
+                // previous event's S phase (or at start-up): the generator is off the critical path
+                const double u1 = s_upair[s_nevents & 1][0];
+                if (lane == 0) {
+                    s_u2 = s_upair[s_nevents & 1][1];
+                    s_psum = Psum;
+                }
                 double number = u1 * Psum;
                 double prev;
                 int ts = (Psum > 0.0) ? warp_pick_256(sc, v, number, &prev) : -1;
+                EV_TICK(8);
                 long long r = -1;
                 if (ts >= 0) {
                     number = number - prev;
@@ -433,220 +462,170 @@ __global__ void __launch_bounds__(EV_THREADS, 1) event_loop_kernel(EvLoopArgs a)
                     int nb0 = -1, nb1 = -1, ty0 = KMCB200_NULL_EVENT, ty1 = KMCB200_NULL_EVENT;
                     if (lane < nn) { p0 = a.prob[base + lane]; nb0 = a.neigh[base + lane]; ty0 = a.type[base + lane]; }
                     if (lane + 32 < nn) { p1 = a.prob[base + lane + 32]; nb1 = a.neigh[base + lane + 32]; ty1 = a.type[base + lane + 32]; }
-                    int rp = 0;
-                    if (lane < 2) rp = a.rev_ptr[r + lane];
                     unsigned m0 = __ballot_sync(KMC_FULL_MASK, p0 > 0.0), m1 = __ballot_sync(KMC_FULL_MASK, p1 > 0.0);
                     int seln = -1, lastn = -1;
                     double acc = 0.0;
-                    bool first = true;
                     // adding an exact zero never changes acc, so only non-zero slots can make acc exceed number
                     unsigned long long mm = ((unsigned long long)m1 << 32) | m0;
                     while (mm) {
                         int n = __ffsll((long long)mm) - 1;
                         mm &= mm - 1;
                         double pv = __shfl_sync(KMC_FULL_MASK, (n < 32) ? p0 : p1, n & 31);
-                        acc = first ? (0.0 + pv) : (acc + pv);
-                        first = false;
+                        acc = acc + pv;  // first term: 0.0 + pv == pv
                         lastn = n;
                         if (acc > number) { seln = n; break; }
                     }
                     if (seln < 0) seln = lastn;
                     EV_TICK(11);
                     if (seln >= 0) {
-                        const int j = __shfl_sync(KMC_FULL_MASK, (seln < 32) ? nb0 : nb1, seln & 31);
-                        const int ty = __shfl_sync(KMC_FULL_MASK, (seln < 32) ? ty0 : ty1, seln & 31);
-                        const int i = (int)r;
-                        int rj = 0;
-                        if (lane >= 2 && lane < 4) rj = a.rev_ptr[j + lane - 2];
-                        if (lane == 0) {
-                            int ne = s_nevents;
-                            if (ne < a.log_cap) {
-                                a.log[4 * ne + 0] = i; a.log[4 * ne + 1] = j; a.log[4 * ne + 2] = ty;
-                                a.log[4 * ne + 3] = (int)(base + seln);
-                                a.log_psum[ne] = Psum;
-                            }
-                            // execute_event: kmc_events.cu:305-328
-                            if (ty == KMCB200_VACANCY_GENERATION) {
-                                a.element[i] = KMCB200_OXYGEN_DEFECT; a.element[j] = KMCB200_VACANCY;
-                                a.charge[i] = -2; a.charge[j] = 2;
-                            } else if (ty == KMCB200_VACANCY_RECOMBINATION) {
-                                a.element[i] = KMCB200_DEFECT; a.element[j] = KMCB200_O;
-                                a.charge[i] = 0; a.charge[j] = 0;
-                            } else if (ty == KMCB200_VACANCY_DIFFUSION || ty == KMCB200_ION_DIFFUSION) {
-                                int e_i = a.element[i], e_j = a.element[j], q_i = a.charge[i], q_j = a.charge[j];
-                                a.element[i] = e_j; a.element[j] = e_i;
-                                a.charge[i] = q_j; a.charge[j] = q_i;
-                            }
-                        }
-                        if (lane < 2) s_rev[lane] = rp;
-                        if (lane >= 2 && lane < 4) s_rev[lane] = rj;
-                        ei = i;
-                        ej = j;
+                        ej = __shfl_sync(KMC_FULL_MASK, (seln < 32) ? nb0 : nb1, seln & 31);
+                        ety = __shfl_sync(KMC_FULL_MASK, (seln < 32) ? ty0 : ty1, seln & 31);
+                        ei = (int)r;
+                        eslot = (int)(base + seln);
                     }
-                }
-                EV_TICK(12);
-                // ---- residence time (kmc_events.cu:515) ----------------------------------------------------
-                if (lane == 0) {
-                    double u2 = mt_next_double(mt, mt_pos);
-                    s_event_time = -log(u2) / Psum;
-                    s_nevents = s_nevents + 1;
-                    s_mtpos = mt_pos;
                 }
             }
             if (lane == 0) {
                 s_stop = !go;
-                s_i = ei;
-                s_j = ej;
-                if (ei >= 0) {
-                    rows_list[0] = ei;
-                    rows_list[1] = ej;
-                    n_rows = 2;
-                } else {
-                    n_rows = 0;
-                }
+                s_i = ei; s_j = ej; s_ty = ety; s_slot = eslot;
+                n_rows = 0;
+                n_chunks = 0;
+                n_supers = 0;
             }
         }
         __syncthreads();
         EV_TICK(0);
         if (s_stop) break;
         const int ei = s_i, ej = s_j;
+        // =============================== Z: zero-out + apply + residence time ================================
+        if (tid == EV_THREADS - 1) {  // residence time (kmc_events.cu:515)
+            s_event_time = -log(s_u2) / s_psum;
+            s_nevents = s_nevents + 1;
+        }
         if (ei >= 0) {
-            // ---- zero-out (zero_out_events_split, kmc_events.cu:247-266) through the reverse index.  Padded slots
-            // already hold rate 0 / NULL_EVENT, so rows ei and ej are cleared entirely.
-            if (tid < 2 * nn) {
-                long long sl = (long long)((tid < nn) ? ei : ej) * nn + (tid < nn ? tid : tid - nn);
-                a.prob[sl] = 0.0;
-                a.type[sl] = KMCB200_NULL_EVENT;
+            if (tid == EV_THREADS - 32) {  // execute_event: kmc_events.cu:305-328
+                const int i = ei, j = ej, ty = s_ty;
+                if (ty == KMCB200_VACANCY_GENERATION) {
+                    a.element[i] = KMCB200_OXYGEN_DEFECT; a.element[j] = KMCB200_VACANCY;
+                    a.charge[i] = -2; a.charge[j] = 2;
+                } else if (ty == KMCB200_VACANCY_RECOMBINATION) {
+                    a.element[i] = KMCB200_DEFECT; a.element[j] = KMCB200_O;
+                    a.charge[i] = 0; a.charge[j] = 0;
+                } else if (ty == KMCB200_VACANCY_DIFFUSION || ty == KMCB200_ION_DIFFUSION) {
+                    int e_i = a.element[i], e_j = a.element[j], q_i = a.charge[i], q_j = a.charge[j];
+                    a.element[i] = e_j; a.element[j] = e_i;
+                    a.charge[i] = q_j; a.charge[j] = q_i;
+                }
             }
-            {
-                const int b0 = s_rev[0], n0 = s_rev[1] - b0, b1 = s_rev[2], n1 = s_rev[3] - b1;
-                for (int q = tid; q < n0 + n1; q += EV_THREADS) {
-                    int sl = (q < n0) ? a.rev_slot[b0 + q] : a.rev_slot[b1 + (q - n0)];
+            // zero-out (zero_out_events_split, kmc_events.cu:247-266).  Padded slots already hold rate 0 / NULL_EVENT,
+            // so rows ei and ej are cleared entirely; slots of other rows pointing at ei / ej come from the reverse index.
+            if (tid < 2 * REV_STRIDE) {
+                const int which = tid / REV_STRIDE, q = tid % REV_STRIDE;
+                const int s_site = which ? ej : ei;
+                if (q < nn) {
+                    long long sl = (long long)s_site * nn + q;
                     a.prob[sl] = 0.0;
                     a.type[sl] = KMCB200_NULL_EVENT;
-                    int rr = sl / nn;
-                    if (rr != ei && rr != ej && smem_set_insert(row_set, 2047, rr)) {
-                        int pos = atomicAdd(&n_rows, 1);
-                        if (pos < MAX_DIRTY) rows_list[pos] = rr;
-                        else s_error = 1;
+                }
+                int sl = a.rev[(size_t)s_site * REV_STRIDE + q];
+                int rr = -1;
+                if (sl >= 0) {
+                    // a slot that already holds rate 0 does not change its row: only rows that lose a non-zero rate need
+                    // their sums repaired (their recomputed sums would be bit-identical anyway)
+                    double oldp = a.prob[sl];
+                    a.type[sl] = KMCB200_NULL_EVENT;
+                    if (oldp != 0.0) {
+                        a.prob[sl] = 0.0;
+                        rr = sl / nn;
+                    }
+                } else if (q == REV_STRIDE - 1) {
+                    rr = s_site;  // the event's own rows (their sums become 0)
+                }
+                if (rr >= 0) {
+                    int pos = atomicAdd(&n_rows, 1);
+                    rows_list[pos] = rr;
+                    if (smem_set_insert(chunk_set, 1023, rr >> 8)) {
+                        chunk_list[atomicAdd(&n_chunks, 1)] = rr >> 8;
+                        if (atomicExch(&super_flag[rr >> 16], 1) == 0) super_list[atomicAdd(&n_supers, 1)] = rr >> 16;
                     }
                 }
             }
-            __syncthreads();
-            EV_TICK(1);
-            const int nd = min(n_rows, MAX_DIRTY);
+        }
+        __syncthreads();
+        EV_TICK(1);
+        if (ei >= 0) {
+            if (tid == 0) {  // event log (i, j, type, slot) + Psum before the event
+                int ne = s_nevents - 1;
+                if (ne < a.log_cap) {
+                    a.log[4 * ne + 0] = ei; a.log[4 * ne + 1] = ej; a.log[4 * ne + 2] = s_ty; a.log[4 * ne + 3] = s_slot;
+                    a.log_psum[ne] = s_psum;
+                }
+            }
+            const int nd = n_rows, nc = n_chunks;
 #ifdef KMC_EV_PROFILE
-            if (tid == 0) ph[14] += nd;
+            if (tid == 0) { ph[14] += nd; ph[15] += nc; }
 #endif
-            // ---- repair row sums: one warp per touched row, 4 rows in flight per warp (butterfly row sum) ------------
-            for (int base = 2; base < nd; base += NW * 4) {
-                double p0[4], p1[4];
-                int rr[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    int q = base + u * NW + warp;
-                    rr[u] = (q < nd) ? rows_list[q] : -1;
-                    p0[u] = 0.0; p1[u] = 0.0;
-                    if (rr[u] >= 0) {
-                        const long long b = (long long)rr[u] * nn;
-                        if (lane < nn) p0[u] = a.prob[b + lane];
-                        if (lane + 32 < nn) p1[u] = a.prob[b + lane + 32];
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (rr[u] < 0) continue;
-                    double sacc = warp_row_sum(p0[u], p1[u]);
-                    if (lane == 0) {
-                        a.rowsum[rr[u]] = sacc;
-                        if (smem_set_insert(chunk_set, 2047, rr[u] >> 3)) chunk_list[atomicAdd(&n_chunks, 1)] = rr[u] >> 3;
-                    }
-                }
-            }
-            if (tid < 2) {  // rows ei / ej are entirely zero now
-                int r2 = rows_list[tid];
-                a.rowsum[r2] = 0.0;
-                if (smem_set_insert(chunk_set, 2047, r2 >> 3)) chunk_list[atomicAdd(&n_chunks, 1)] = r2 >> 3;
+            // =============================== R1: row sums, one warp per touched row ==================================
+            // (duplicates in rows_list recompute the same value)
+            for (int q = warp; q < nd; q += NW) {
+                const int rr = rows_list[q];
+                const long long pb = (long long)rr * nn;
+                double p0 = (lane < nn) ? a.prob[pb + lane] : 0.0;
+                double p1 = (lane + 32 < nn) ? a.prob[pb + lane + 32] : 0.0;
+                double sacc = warp_row_sum(p0, p1);
+                if (lane == 0) a.rowsum[rr] = sacc;
             }
             __syncthreads();
             EV_TICK(2);
-            // ---- repair the group-of-8 totals (sequential part of scan_256): one thread per touched group ------------
-            const int ngrp_d = n_chunks;  // chunk_list holds unique GROUP ids (row >> 3) here
-#ifdef KMC_EV_PROFILE
-            if (tid == 0) ph[15] += ngrp_d;
-#endif
-            for (int q = tid; q < ngrp_d; q += EV_THREADS) {
-                const int g = chunk_list[q];
-                const long long rb = (long long)g * 8;
-                double w[8];
-                if (rb + 8 <= a.N) {
-                    const double2 *src2 = reinterpret_cast<const double2 *>(a.rowsum + rb);
+            // =============================== R2: chunk sums, one warp per touched chunk ==============================
+            for (int q = warp; q < nc; q += NW) {
+                const int c = chunk_list[q];
+                Scan256 sc;
+                const long long rbase = (long long)c * 256 + 8 * lane;
+                if (rbase + 8 <= a.N) {
+                    const double2 *src2 = reinterpret_cast<const double2 *>(a.rowsum + rbase);
 #pragma unroll
-                    for (int m = 0; m < 4; ++m) { double2 t2 = src2[m]; w[2 * m] = t2.x; w[2 * m + 1] = t2.y; }
+                    for (int k = 0; k < 4; ++k) { double2 t2 = src2[k]; sc.a[2 * k] = t2.x; sc.a[2 * k + 1] = t2.y; }
                 } else {
 #pragma unroll
-                    for (int m = 0; m < 8; ++m) w[m] = (rb + m < a.N) ? a.rowsum[rb + m] : 0.0;
+                    for (int k = 0; k < 8; ++k) sc.a[k] = (rbase + k < a.N) ? a.rowsum[rbase + k] : 0.0;
                 }
-                double acc = w[0];
-#pragma unroll
-                for (int m = 1; m < 8; ++m) acc = acc + w[m];
-                a.gtot[g] = acc;
-            }
-            __syncthreads();
-            EV_TICK(5);
-            // ---- chunk sums: Kogge-Stone over the 32 group totals of the chunk; one warp per touched group's chunk
-            // (duplicate chunks write the same value), 4 in flight
-            for (int base = 0; base < ngrp_d; base += NW * 4) {
-                double tv[4];
-                int cc[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    int q = base + u * NW + warp;
-                    cc[u] = (q < ngrp_d) ? (chunk_list[q] >> 5) : -1;
-                    tv[u] = (cc[u] >= 0) ? a.gtot[(long long)cc[u] * 32 + lane] : 0.0;
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (cc[u] < 0) continue;
-                    double S = kmc_warp_inclusive_scan(tv[u]);
-                    if (lane == 31) {
-                        cs[cc[u]] = S;
-                        if (a.chunks_in_smem) a.chunksum[cc[u]] = S;
-                        super_flag[cc[u] >> 8] = 1;
-                    }
+                warp_scan_256(sc);
+                if (lane == 0) {
+                    cs[c] = sc.total;
+                    if (a.chunks_in_smem) a.chunksum[c] = sc.total;
                 }
             }
-            __syncthreads();
-            EV_TICK(3);
-            // ---- repair super sums: one warp per touched super ------------------------------------------------------
-            for (int sidx = warp; sidx < (int)a.nsuper; sidx += NW) {
-                if (super_flag[sidx]) {
-                    Scan256 sc;
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        long long c = (long long)sidx * 256 + 8 * lane + k;
-                        sc.a[k] = (c < a.nchunk) ? cs[c] : 0.0;
-                    }
-                    warp_scan_256(sc);
-                    if (lane == 0) {
-                        ss[sidx] = sc.total;
-                        a.supersum[sidx] = sc.total;
-                        super_flag[sidx] = 0;
-                    }
-                }
-            }
-            // reset the de-duplication sets
-            for (int q = tid; q < 2048; q += EV_THREADS) { row_set[q] = -1; chunk_set[q] = -1; }
-            if (tid == 0) { n_chunks = 0; }
             __syncthreads();
             EV_TICK(4);
+            // =============================== U: super sums, one warp per touched super ==============================
+            const int nsd = n_supers;
+            for (int q = warp; q < nsd; q += NW) {
+                const int sidx = super_list[q];
+                Scan256 sc;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    long long c = (long long)sidx * 256 + 8 * lane + k;
+                    sc.a[k] = (c < a.nchunk) ? cs[c] : 0.0;
+                }
+                warp_scan_256(sc);
+                if (lane == 0) {
+                    ss[sidx] = sc.total;
+                    a.supersum[sidx] = sc.total;
+                    super_flag[sidx] = 0;
+                }
+            }
+            for (int q = tid; q < 1024; q += EV_THREADS) chunk_set[q] = -1;
+            __syncthreads();
+            EV_TICK(3);
         }
     }
-    for (int q = tid; q < 624; q += EV_THREADS) a.mt_state[q] = mt[q];
+    // the pair drawn for the event that did not happen is handed back to the generator
+    for (int q = tid; q < 624; q += EV_THREADS) a.mt_state[q] = s_backup_valid ? mt_backup[q] : mt[q];
     if (tid == 0) {
-        a.mt_state[624] = (unsigned)s_mtpos;
+        a.mt_state[624] = (unsigned)s_pos_before;
         a.result->event_time = s_event_time;
-        a.result->psum_last = 0.0;
+        a.result->psum_last = s_psum;
         a.result->n_events = s_nevents;
         a.result->error = s_error;
 #ifdef KMC_EV_PROFILE
@@ -685,10 +664,8 @@ extern "C" int kmcb200_events_create(kmcb200_ctx *ctx, int N, int nn, const int 
     A((void **)&ev->prob, (size_t)total * sizeof(double));
     A((void **)&ev->type, (size_t)total);
     A((void **)&ev->rowsum, (size_t)N * sizeof(double));
-    A((void **)&ev->gtot, (size_t)(ev->nchunk * 32) * sizeof(double));
     A((void **)&ev->chunksum, (size_t)ev->nchunk * sizeof(double));
     A((void **)&ev->supersum, (size_t)MAX_SUPER * sizeof(double));
-    A((void **)&ev->rev_ptr, (size_t)(N + 1) * sizeof(int));
     A((void **)&ev->mt, 640 * sizeof(unsigned));
     A((void **)&ev->log, (size_t)ev->log_cap * 4 * sizeof(int));
     A((void **)&ev->log_psum, (size_t)ev->log_cap * sizeof(double));
@@ -700,25 +677,30 @@ extern "C" int kmcb200_events_create(kmcb200_ctx *ctx, int N, int nn, const int 
     }
     // reverse neighbour index: for each site s the slots (r,n) with neigh[r][n] == s (static)
     int *fill = nullptr;
-    int rc = kmc_scratch(ctx, 8, (size_t)(N + 1) * sizeof(int), (void **)&fill);
+    int rc = kmc_scratch(ctx, 8, (size_t)(N + 2) * sizeof(int), (void **)&fill);
     if (rc) { kmcb200_events_destroy(ev); return rc; }
-    cudaMemsetAsync(ev->rev_ptr, 0, (size_t)(N + 1) * sizeof(int), ctx->stream);
-    cudaMemsetAsync(fill, 0, (size_t)(N + 1) * sizeof(int), ctx->stream);
+    if (cudaMalloc((void **)&ev->rev, (size_t)N * REV_STRIDE * sizeof(int)) != cudaSuccess) {
+        kmc_set_error("cudaMalloc(reverse index) failed");
+        kmcb200_events_destroy(ev);
+        return KMCB200_E_CUDA;
+    }
+    cudaMemsetAsync(ev->rev, 0xff, (size_t)N * REV_STRIDE * sizeof(int), ctx->stream);
+    cudaMemsetAsync(fill, 0, (size_t)(N + 2) * sizeof(int), ctx->stream);
     unsigned blocks = (unsigned)((total + 255) / 256);
     kmc_count_launch();
-    rev_count_kernel<<<blocks, 256, 0, ctx->stream>>>(neigh, total, ev->rev_ptr);
-    rc = kmc_exclusive_scan_i32(ctx, ev->rev_ptr, ev->rev_ptr, (long long)N + 1, 4);
-    if (rc) { kmcb200_events_destroy(ev); return rc; }
-    int M = 0;
-    cudaMemcpyAsync(&M, ev->rev_ptr + N, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
-    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess || cudaMalloc((void **)&ev->rev_slot, (size_t)(M + 1) * sizeof(int)) != cudaSuccess) {
+    rev_fill_kernel<<<blocks, 256, 0, ctx->stream>>>(neigh, total, fill, ev->rev, fill + N + 1);
+    int ovf = 0;
+    cudaMemcpyAsync(&ovf, fill + N + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
         kmc_set_error("reverse index build failed: %s", cudaGetErrorString(cudaGetLastError()));
         kmcb200_events_destroy(ev);
         return KMCB200_E_CUDA;
     }
-    kmc_count_launch();
-    rev_fill_kernel<<<blocks, 256, 0, ctx->stream>>>(neigh, total, ev->rev_ptr, fill, ev->rev_slot);
-    if (cudaGetLastError() != cudaSuccess) { kmc_set_error("rev_fill launch failed"); kmcb200_events_destroy(ev); return KMCB200_E_CUDA; }
+    if (ovf) {
+        kmc_set_error("a site is listed as neighbour by more than %d rows", REV_STRIDE);
+        kmcb200_events_destroy(ev);
+        return KMCB200_E_CAPACITY;
+    }
     *ev_out = ev;
     return kmcb200_rng_seed(ev, 1u);  // rnd_seed_kmc = 1, src/structure_input.h:8
 }
@@ -726,8 +708,8 @@ extern "C" int kmcb200_events_create(kmcb200_ctx *ctx, int N, int nn, const int 
 extern "C" int kmcb200_events_destroy(kmcb200_events *ev) {
     if (!ev) return 0;
     if (ev->ctx) cudaStreamSynchronize(ev->ctx->stream);
-    cudaFree(ev->prob); cudaFree(ev->type); cudaFree(ev->rowsum); cudaFree(ev->gtot); cudaFree(ev->chunksum); cudaFree(ev->supersum);
-    cudaFree(ev->rev_ptr); cudaFree(ev->rev_slot); cudaFree(ev->mt); cudaFree(ev->log); cudaFree(ev->log_psum);
+    cudaFree(ev->prob); cudaFree(ev->type); cudaFree(ev->rowsum); cudaFree(ev->chunksum); cudaFree(ev->supersum);
+    cudaFree(ev->rev); cudaFree(ev->mt); cudaFree(ev->log); cudaFree(ev->log_psum);
     cudaFree(ev->result);
     delete ev;
     return 0;
@@ -804,7 +786,7 @@ extern "C" int kmcb200_build_event_list(kmcb200_ctx *ctx, kmcb200_events *ev, in
     build_rates_kernel<<<(unsigned)ev->nchunk, 256, 0, ctx->stream>>>(N, nn, neigh, site_layer, kT, freq, sigma, k, x, y,
                                                                      z, site_potential_charge, site_element,
                                                                      site_charge, ev->energies, ev->prob, ev->type,
-                                                                     ev->rowsum, ev->gtot, ev->chunksum);
+                                                                     ev->rowsum, ev->chunksum);
     KMC_CUDA(cudaGetLastError());
     kmc_count_launch();
     super_sums_kernel<<<(unsigned)ev->nsuper, 32, 0, ctx->stream>>>(ev->chunksum, ev->nchunk, ev->supersum);
@@ -823,7 +805,7 @@ extern "C" int kmcb200_execute_kmc_step(kmcb200_ctx *ctx, kmcb200_events *ev, in
     a.N = N; a.nn = nn; a.nchunk = ev->nchunk; a.nsuper = ev->nsuper;
     a.neigh = neigh; a.prob = ev->prob; a.type = ev->type;
     a.rowsum = ev->rowsum; a.chunksum = ev->chunksum; a.supersum = ev->supersum;
-    a.rev_ptr = ev->rev_ptr; a.rev_slot = ev->rev_slot;
+    a.rev = ev->rev;
     a.element = site_element; a.charge = site_charge;
     a.mt_state = ev->mt;
     a.inv_freq_threshold = 1 / freq;  // kmc_events.cu:448
@@ -831,7 +813,6 @@ extern "C" int kmcb200_execute_kmc_step(kmcb200_ctx *ctx, kmcb200_events *ev, in
     a.log = ev->log; a.log_psum = ev->log_psum; a.log_cap = ev->log_cap;
     a.result = ev->result;
     a.phase_cycles = nullptr;
-    a.gtot = ev->gtot;
 #ifdef KMC_EV_PROFILE
     KMC_TRY(kmc_scratch(ctx, 5, 16 * sizeof(long long), (void **)&a.phase_cycles));
 #endif
