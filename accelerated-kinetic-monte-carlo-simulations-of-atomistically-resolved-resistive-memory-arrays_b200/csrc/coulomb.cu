@@ -58,7 +58,7 @@ struct __align__(16) Source {
 __global__ void charged_scatter_kernel(const int *__restrict__ charge, const int *__restrict__ element,
                                        const double *__restrict__ x, const double *__restrict__ y,
                                        const double *__restrict__ z, int N, const int *__restrict__ offs,
-                                       const int *__restrict__ site_cell, Source *__restrict__ src,
+                                       const int *__restrict__ site_cell, int ny, int nz, Source *__restrict__ src,
                                        int *__restrict__ src_cell) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
@@ -67,7 +67,8 @@ __global__ void charged_scatter_kernel(const int *__restrict__ charge, const int
         s.x = x[i]; s.y = y[i]; s.z = z[i]; s.charge = charge[i]; s.idx = i;
         int o = offs[i];
         src[o] = s;
-        src_cell[o] = site_cell[i];
+        const int sc = site_cell[i];
+        src_cell[o] = (sc / (ny * nz)) | (((sc / nz) % ny) << 10) | ((sc % nz) << 20);  // packed (a, b, d)
     }
 }
 
@@ -104,31 +105,40 @@ __global__ void block_map_kernel(const int *__restrict__ blk_start, int ncell, i
 }
 
 // ---- per step: ascending-j list of the charged sources in the 27-cell neighbourhood of every cell ----------
-// One thread per cell walks the (ascending j) compacted source list; every lane of a warp reads the same source
-// cell id (broadcast), so the walk costs one L1 hit per source.
+// One WARP per cell walks the (ascending j) compacted source list 32 sources at a time; ballot + popc give each
+// matching source its ordered position, so the per-cell lists stay in ascending j.  Source cells are stored as
+// packed (a, b, d) coordinates (10 bits each) to keep the inner loop division free.
 template <bool FILL>
 __global__ void __launch_bounds__(128) cell_sources_kernel(int nx, int ny, int nz, const int *__restrict__ src_cell,
                                                           const int *__restrict__ nsrc_ptr,
                                                           const int *__restrict__ cell_tstart,
                                                           int *__restrict__ cnt_or_start, int *__restrict__ lists) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    int ncell = nx * ny * nz;
-    bool active = c < ncell && (cell_tstart[c + 1] > cell_tstart[c]);  // cells without targets need no list
-    int cc = c < ncell ? c : 0;
-    int a = cc / (ny * nz), b = (cc / nz) % ny, d = cc % nz;
-    const int Q = *nsrc_ptr;
-    int n = 0;
-    int out = FILL ? cnt_or_start[cc] : 0;
-    for (int q = 0; q < Q; ++q) {
-        int sc = src_cell[q];
-        int sa = sc / (ny * nz), sb = (sc / nz) % ny, sd = sc % nz;
-        bool nb = active && (abs(sa - a) <= 1) && (abs(sb - b) <= 1) && (abs(sd - d) <= 1);
-        if (nb) {
-            if (FILL) lists[out + n] = q;
-            n++;
-        }
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int ncell = nx * ny * nz;
+    if (c > ncell) return;
+    if (c == ncell) {
+        if (!FILL && lane == 0) cnt_or_start[c] = 0;
+        return;
     }
-    if (!FILL && c <= ncell) cnt_or_start[c] = (c < ncell) ? n : 0;
+    const bool active = cell_tstart[c + 1] > cell_tstart[c];  // cells without targets need no list
+    const int a = c / (ny * nz), b = (c / nz) % ny, d = c % nz;
+    const int Q = active ? *nsrc_ptr : 0;
+    int n = 0;
+    const int out = FILL ? cnt_or_start[c] : 0;
+    for (int q0 = 0; q0 < Q; q0 += 32) {
+        const int q = q0 + lane;
+        bool nb = false;
+        if (q < Q) {
+            const int sc = src_cell[q];
+            const int sa = sc & 1023, sb = (sc >> 10) & 1023, sd = (sc >> 20) & 1023;
+            nb = (abs(sa - a) <= 1) && (abs(sb - b) <= 1) && (abs(sd - d) <= 1);
+        }
+        const unsigned m = __ballot_sync(KMC_FULL_MASK, nb);
+        if (FILL && nb) lists[out + n + __popc(m & ((1u << lane) - 1u))] = q;
+        n += __popc(m);
+    }
+    if (!FILL && lane == 0) cnt_or_start[c] = n;
 }
 
 constexpr int CT = 128;    // target sites per CTA
@@ -224,6 +234,10 @@ static int build_plan(kmcb200_ctx *ctx, CoulombPlan &P, int N, const double *x, 
     CellGridDev g;
     KMC_TRY(kmc_build_cellgrid(ctx, x, y, z, 0, N, cutoff, 0, nullptr, &g));  // scratch slots 0,1 hold start/items
     int ncell = g.nx * g.ny * g.nz;
+    if (g.nx >= 1024 || g.ny >= 1024 || g.nz >= 1024) {
+        kmc_set_error("Coulomb cell grid %dx%dx%d exceeds 1023 cells per axis", g.nx, g.ny, g.nz);
+        return KMCB200_E_CAPACITY;
+    }
     KMC_CUDA(cudaMalloc(&P.site_cell, (size_t)N * sizeof(int)));
     KMC_CUDA(cudaMalloc(&P.cell_tstart, (size_t)(ncell + 1) * sizeof(int)));
     KMC_CUDA(cudaMalloc(&P.titems, (size_t)N * sizeof(int)));
@@ -284,11 +298,11 @@ extern "C" int kmcb200_poisson_gridless(kmcb200_ctx *ctx, int N, const double *x
     KMC_TRY(kmc_scratch(ctx, 7, (size_t)(Q + 1) * sizeof(Source), (void **)&src));
     KMC_TRY(kmc_scratch(ctx, 8, (size_t)(Q + 1) * sizeof(int), (void **)&src_cell));
     kmc_count_launch();
-    charged_scatter_kernel<<<(N + 255) / 256, 256, 0, ctx->stream>>>(charge, element, x, y, z, N, offs, P.site_cell, src,
-                                                                    src_cell);
+    charged_scatter_kernel<<<(N + 255) / 256, 256, 0, ctx->stream>>>(charge, element, x, y, z, N, offs, P.site_cell, P.g.ny,
+                                                                    P.g.nz, src, src_cell);
     KMC_CUDA(cudaGetLastError());
     // 2. per-cell neighbourhood source lists (count, scan, fill)
-    unsigned cb = (unsigned)((P.ncell + 1 + 127) / 128);
+    unsigned cb = (unsigned)(((long long)(P.ncell + 1) * 32 + 127) / 128);  // one warp per cell
     kmc_count_launch();
     cell_sources_kernel<false><<<cb, 128, 0, ctx->stream>>>(P.g.nx, P.g.ny, P.g.nz, src_cell, offs + N, P.cell_tstart,
                                                            P.list_start, nullptr);

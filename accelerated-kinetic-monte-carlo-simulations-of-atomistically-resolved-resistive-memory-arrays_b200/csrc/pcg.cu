@@ -55,8 +55,26 @@ __global__ void __launch_bounds__(CH) spmv_kernel(int rows, const int *__restric
         int r = row0 + rl;
         double acc = 0.0;
         if (r < rows) {
-            int s = row_ptr[r], e = row_ptr[r + 1];
-            for (int k = s + lane; k < e; k += L) acc = fma(__ldcs(val + k), __ldg(xg + __ldcs(col + k)), acc);
+            const int s = row_ptr[r], e = row_ptr[r + 1];
+            // all of this lane's entries (k = s+lane, s+lane+L, ...) are loaded before the FMA chain starts, so a lane
+            // keeps up to DEPTH (val, col, x) triples in flight instead of one; the FMA order is unchanged.
+            constexpr int DEPTH = 7;  // covers rows of up to 56 entries in one trip
+            for (int k0 = s + lane; k0 < e; k0 += L * DEPTH) {
+                double v[DEPTH], xv[DEPTH];
+                int c[DEPTH];
+#pragma unroll
+                for (int t = 0; t < DEPTH; ++t) {
+                    const int k = k0 + t * L;
+                    const bool ok = k < e;
+                    v[t] = ok ? __ldcs(val + k) : 0.0;
+                    c[t] = ok ? __ldcs(col + k) : -1;
+                }
+#pragma unroll
+                for (int t = 0; t < DEPTH; ++t) xv[t] = (c[t] >= 0) ? __ldg(xg + c[t]) : 0.0;
+#pragma unroll
+                for (int t = 0; t < DEPTH; ++t)
+                    if (c[t] >= 0) acc = fma(v[t], xv[t], acc);
+            }
         }
 #pragma unroll
         for (int off = L / 2; off >= 1; off >>= 1) acc = acc + __shfl_xor_sync(KMC_FULL_MASK, acc, off);

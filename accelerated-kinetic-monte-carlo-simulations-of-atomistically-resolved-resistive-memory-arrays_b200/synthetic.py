@@ -7,6 +7,8 @@ contact layers (src/potential_solver_gpu.cu:855-861).
 
   order="file"    : images emitted site-major -> the 5 nm file's block structure is preserved (wide K bandwidth)
   order="xsorted" : interior sites stably sorted by x (narrow halo for row-sharded solves); contacts stay first/last
+  order="lex"     : interior sites sorted by (x, y, z) lexicographically, the scheme of the shipped file's crystalline
+                    blocks (narrow halo AND neighbouring rows share neighbours)
 """
 from __future__ import annotations
 
@@ -36,6 +38,14 @@ def tile_structure(base: Structure, ty: int, tz: int, order: str = "file", vacan
         n = len(x)
         interior = np.arange(NL, n - NR)
         perm = interior[np.argsort(x[interior], kind="stable")]
+        full = np.concatenate([np.arange(NL), perm, np.arange(n - NR, n)])
+        x, y, z, el = x[full], y[full], z[full], el[full]
+    elif order == "lex":
+        # (x, y, z) lexicographic order of the interior sites -- how the crystalline parts of the shipped 5 nm file are
+        # ordered (z fastest, then y, then x); contacts stay first / last
+        n = len(x)
+        interior = np.arange(NL, n - NR)
+        perm = interior[np.lexsort((z[interior], y[interior], x[interior]))]
         full = np.concatenate([np.arange(NL), perm, np.arange(n - NR, n)])
         x, y, z, el = x[full], y[full], z[full], el[full]
     elif order != "file":

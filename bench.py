@@ -74,10 +74,12 @@ def build_workload(kmc, name):
     syn = importlib.import_module(PKG + ".synthetic")
     if name == "5nm":
         return kmc.load_structure(PARAM_5NM), "structures/5nm_device (shipped), N=37650"
-    t = {"standin8x8": 8, "standin4x4": 4, "standin2x2": 2, "standin16x16": 16}[name]
-    s = syn.crossbar_standin(PARAM_5NM, t, t, order="file", Vd=15.0, rnd_seed=32)
+    base, _, order = name.partition("_")
+    order = order or "file"
+    t = {"standin8x8": 8, "standin4x4": 4, "standin2x2": 2, "standin16x16": 16}[base]
+    s = syn.crossbar_standin(PARAM_5NM, t, t, order=order, Vd=15.0, rnd_seed=32)
     return s, (f"40nm_crossbar stand-in: {t}x{t} lateral tiling of the shipped 5nm cell, N={s.N}, "
-               f"num_atoms_first_layer={s.N_left}, Vd=15, file order")
+               f"num_atoms_first_layer={s.N_left}, Vd=15, site order '{order}'")
 
 
 # ------------------------------------------------------------------------------------------------
