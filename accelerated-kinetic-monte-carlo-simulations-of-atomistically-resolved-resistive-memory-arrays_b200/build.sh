@@ -8,7 +8,7 @@ FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 --fmad=false -std=c
 mkdir -p "$HERE/build"
 objs=""
 pids=""
-for f in ctx scan lists kmat pcg coulomb events comm; do
+for f in ctx scan lists kmat spmv_plan pcg coulomb events comm; do
   src="$HERE/csrc/$f.cu"
   [ -f "$src" ] || continue
   obj="$HERE/build/$f.o"
@@ -29,5 +29,5 @@ if [ ! -f "$obj" ] || [ "$HERE/host/host_model.cpp" -nt "$obj" ] || [ "$HERE/../
 fi
 objs="$objs $obj"
 for p in $pids; do wait $p || { echo "build.sh: compilation failed" >&2; exit 1; }; done
-$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT" $objs -cudart static -ccbin /usr/bin/g++
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT" $objs -cudart static -ccbin /usr/bin/g++ -Xlinker --no-undefined
 echo "built $OUT"

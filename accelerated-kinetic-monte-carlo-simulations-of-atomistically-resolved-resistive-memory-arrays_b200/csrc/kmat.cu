@@ -3,6 +3,8 @@
 // :438-454 (calc_rhs_for_A), :774-830 (reduce_rows_into_diag, insert_into_diag, inverse_diag), driver :893-1029.
 // The reference runs 7 thread-per-row kernels + 5 memsets per step; here one kernel with 8 lanes per row writes
 // values, diagonal, inverse diagonal and rhs in a single pass over the CSR (coalesced col reads / val writes).
+#include <stdlib.h>
+
 #include "kmat.cuh"
 
 namespace {
@@ -98,6 +100,8 @@ int kmc_kmat_finalize(kmcb200_kmat *K) {
     KMC_CUDA(cudaMalloc(&K->Ap, (size_t)K->rows * sizeof(double)));
     KMC_CUDA(cudaMalloc(&K->z, (size_t)K->rows * sizeof(double)));
     KMC_CUDA(cudaMemsetAsync(K->p_full, 0, (size_t)K->cols_global * sizeof(double), K->ctx->stream));
+    K->plan_max_unique = 0;
+    if (getenv("KMCB200_SPMV_STAGED")) return kmc_build_spmv_plan(K);  // opt-in experiment, see pcg.cu
     return 0;
 }
 
@@ -134,6 +138,7 @@ extern "C" int kmcb200_kmat_destroy(kmcb200_kmat *K) {
         cudaFree(K->inv_diag); cudaFree(K->rhs);
     }
     cudaFree(K->p_full); cudaFree(K->Ap); cudaFree(K->z); cudaFree(K->site_class);
+    cudaFree(K->u_ptr); cudaFree(K->u_col); cudaFree(K->lcol);
     delete K;
     return 0;
 }

@@ -23,6 +23,13 @@ struct kmcb200_kmat {
     unsigned char *site_class = nullptr;  // N bytes, (re)built by assemble
     size_t site_class_cap = 0;
     kmcb200_comm *comm = nullptr;  // nullptr: single GPU
+    // SpMV plan (spmv_plan.cu): per 256-row chunk the sorted unique columns it touches (u_col, CSR-like u_ptr) and a
+    // 16-bit chunk-local column id per non-zero (lcol).  The SpMV stages x[u_col] in shared memory once per chunk and
+    // gathers from there; HBM traffic per non-zero drops from 12 B (val + int32 col) to 10 B (val + uint16 lcol).
+    int *u_ptr = nullptr, *u_col = nullptr;
+    unsigned short *lcol = nullptr;
+    int plan_max_unique = 0;  // 0: no plan (fall back to the direct-gather kernel)
 };
 
-int kmc_kmat_finalize(kmcb200_kmat *K);  // allocates the PCG workspace
+int kmc_kmat_finalize(kmcb200_kmat *K);  // allocates the PCG workspace + builds the SpMV plan
+int kmc_build_spmv_plan(kmcb200_kmat *K);

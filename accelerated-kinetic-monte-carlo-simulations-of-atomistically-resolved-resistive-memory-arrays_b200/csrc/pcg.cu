@@ -5,6 +5,7 @@
 // The reference runs per iteration: 1 rocsparse_spmv per neighbour block, 2 hipblasDdot (each a blocking host
 // round trip + MPI_Allreduce), 3 daxpy, 1 dscal, 1 elementwise = 11 vector streams*... Here: 3 kernels per
 // iteration, all scalars stay on the device, 11 vector streams + the matrix (B_iter = 12 nnz + 108 n bytes).
+#include <stdlib.h>
 #include <string.h>
 
 #include "kmat.cuh"
@@ -74,6 +75,78 @@ __global__ void __launch_bounds__(CH) spmv_kernel(int rows, const int *__restric
 #pragma unroll
                 for (int t = 0; t < DEPTH; ++t)
                     if (c[t] >= 0) acc = fma(v[t], xv[t], acc);
+            }
+        }
+#pragma unroll
+        for (int off = L / 2; off >= 1; off >>= 1) acc = acc + __shfl_xor_sync(KMC_FULL_MASK, acc, off);
+        if (lane == 0) {
+            double pv = 0.0;
+            if (r < rows) {
+                y[r] = acc;
+                if (DOT) pv = xg[row_start + r] * acc;
+            }
+            if (DOT) prod[rl] = pv;
+        }
+    }
+    if (DOT) {
+        __syncthreads();
+        double c = kmc_chunk_reduce_256(prod[threadIdx.x], red);
+        if (threadIdx.x == 0) partials[blockIdx.x] = c;
+        if (last_cta(&st->cnt[0], &flag)) {
+            double tot = kmc_final_reduce(partials, gridDim.x, red);
+            if (threadIdx.x == 0) {
+                st->pAp = tot;
+                st->cnt[0] = 0;
+            }
+        }
+    }
+}
+
+// Shared-memory staged variant: the chunk's unique columns (u_col) are gathered ONCE into shared memory, every
+// non-zero then reads x through its 16-bit chunk-local id.  Same row reduction spec (bit-identical results).
+template <int L, bool DOT>
+__global__ void __launch_bounds__(CH) spmv_staged_kernel(int rows, const int *__restrict__ row_ptr,
+                                                        const unsigned short *__restrict__ lcol,
+                                                        const double *__restrict__ val,
+                                                        const int *__restrict__ u_ptr, const int *__restrict__ u_col,
+                                                        const double *__restrict__ xg, int row_start,
+                                                        double *__restrict__ y, double *__restrict__ partials,
+                                                        CgState *__restrict__ st) {
+    if (DOT && st->done) return;
+    extern __shared__ double xs[];  // the chunk's x window
+    __shared__ double prod[CH];
+    __shared__ double red[8];
+    __shared__ int flag;
+    constexpr int GROUPS = CH / L;
+    const int lane = threadIdx.x % L;
+    const int grp = threadIdx.x / L;
+    const int row0 = blockIdx.x * CH;
+    {
+        const int ub = u_ptr[blockIdx.x], nu = u_ptr[blockIdx.x + 1] - ub;
+        for (int i = threadIdx.x; i < nu; i += CH) xs[i] = __ldg(xg + __ldcs(u_col + ub + i));
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int pass = 0; pass < L; ++pass) {
+        int rl = pass * GROUPS + grp;
+        int r = row0 + rl;
+        double acc = 0.0;
+        if (r < rows) {
+            const int s = row_ptr[r], e = row_ptr[r + 1];
+            constexpr int DEPTH = 7;
+            for (int k0 = s + lane; k0 < e; k0 += L * DEPTH) {
+                double v[DEPTH];
+                int c[DEPTH];
+#pragma unroll
+                for (int t = 0; t < DEPTH; ++t) {
+                    const int k = k0 + t * L;
+                    const bool ok = k < e;
+                    v[t] = ok ? __ldcs(val + k) : 0.0;
+                    c[t] = ok ? (int)__ldcs(lcol + k) : -1;
+                }
+#pragma unroll
+                for (int t = 0; t < DEPTH; ++t)
+                    if (c[t] >= 0) acc = fma(v[t], xs[c[t]], acc);
             }
         }
 #pragma unroll
@@ -234,12 +307,31 @@ int kmc_spmv_launch(kmcb200_ctx *ctx, kmcb200_kmat *K, const double *xg, double 
     constexpr int L = KMCB200_SPMV_LANES;
     unsigned blocks = (unsigned)((K->rows + CH - 1) / CH);
     kmc_count_launch();
-    if (with_dot)
+    const size_t dyn = (size_t)K->plan_max_unique * sizeof(double);
+    // The staged kernel only pays off when the rows of a chunk share columns (reuse >> 1); for the DeviceKMC lattices
+    // the measured reuse is 1.3-1.7 and it is SLOWER (371 us vs 197 us at 62 M nnz), so it is opt-in.
+    if (K->plan_max_unique > 0 && dyn <= 200 * 1024) {
+        static size_t configured = 0;
+        if (dyn > configured) {
+            KMC_CUDA(cudaFuncSetAttribute(spmv_staged_kernel<L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            KMC_CUDA(cudaFuncSetAttribute(spmv_staged_kernel<L, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            configured = dyn;
+        }
+        if (with_dot)
+            spmv_staged_kernel<L, true><<<blocks, CH, dyn, ctx->stream>>>(K->rows, K->row_ptr, K->lcol, K->val, K->u_ptr,
+                                                                         K->u_col, xg, K->row_start, y, ctx->partials,
+                                                                         ctx->cg_state);
+        else
+            spmv_staged_kernel<L, false><<<blocks, CH, dyn, ctx->stream>>>(K->rows, K->row_ptr, K->lcol, K->val, K->u_ptr,
+                                                                          K->u_col, xg, K->row_start, y, ctx->partials,
+                                                                          ctx->cg_state);
+    } else if (with_dot) {
         spmv_kernel<L, true><<<blocks, CH, 0, ctx->stream>>>(K->rows, K->row_ptr, K->col, K->val, xg, K->row_start, y,
                                                             ctx->partials, ctx->cg_state);
-    else
+    } else {
         spmv_kernel<L, false><<<blocks, CH, 0, ctx->stream>>>(K->rows, K->row_ptr, K->col, K->val, xg, K->row_start, y,
                                                              ctx->partials, ctx->cg_state);
+    }
     KMC_CUDA(cudaGetLastError());
     return 0;
 }
