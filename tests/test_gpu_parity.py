@@ -319,3 +319,30 @@ def test_event_loop_all_event_types_small(kmc, ctx, orc):
         assert (to_np(dev.element) == sim.element).all() and (to_np(dev.charge) == sim.charge).all()
         seen |= set(log[:, 2].tolist())
     assert seen >= {1, 2, 3}  # (generation fires in the 5 nm 1000-step fixture: 12 events)
+
+
+def test_cpp_host_driver_reproduces_golden_output(kmc, tmp_path):
+    """The C++ host (host/kmc_main.cpp: reference main() call order through include/gpu_solvers_b200.hpp) run on the
+    shipped 5 nm inputs writes the reference's output files: 'KMC time is:' lines within 1e-3 of output1_0.txt and the
+    final snapshot's elements identical to snapshot_6.xyz."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(kmc.LIB_PATH), "kmc_b200_run")
+    if not os.path.exists(exe):
+        pytest.skip("kmc_b200_run not built")
+    r = subprocess.run([exe, os.path.join(GOLD, "5nm_device", "parameters.txt")], cwd=tmp_path, capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = open(tmp_path / "output1_0.txt").read()
+    mine = [float(l.split(":")[1]) for l in out.split("\n") if l.startswith("KMC time is")]
+    gold = [float(l.split(":")[1]) for l in open(os.path.join(GOLD, "5nm_device", "output1_0.txt")) if l.startswith("KMC time is")]
+    assert len(mine) == len(gold) == 6 and np.allclose(mine, gold, rtol=1e-3)
+    snap = open(tmp_path / "Results_5.000000" / "snapshot_6.xyz").read().split("\n")
+    with gzip.open(os.path.join(GOLD, "5nm_device", "snapshot_6.xyz.gz"), "rt") as f:
+        gsnap = f.read().split("\n")
+    assert [l.split()[0] for l in snap[2:37652]] == [l.split()[0] for l in gsnap[2:37652]]
+    pm = np.array([float(l.split()[4]) for l in snap[2:37652]]); pg = np.array([float(l.split()[4]) for l in gsnap[2:37652]])
+    assert np.abs(pm - pg).max() < 5e-4
+    init = open(tmp_path / "Results_5.000000" / "snapshot_init.xyz").read().split("\n")
+    with gzip.open(os.path.join(GOLD, "5nm_device", "snapshot_init.xyz.gz"), "rt") as f:
+        ginit = f.read().split("\n")
+    assert init[:37652] == ginit[:37652]   # byte-identical initial snapshot (same ostream formatting)
