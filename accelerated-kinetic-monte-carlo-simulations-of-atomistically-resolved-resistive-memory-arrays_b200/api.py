@@ -103,6 +103,14 @@ SIGNATURES = {
     "kmcb200_spmv": (_i, [_vp, _vp, _vp, _vp]),
     "kmcb200_dot": (_i, [_vp, _vp, _vp, _ll, _pd]),
     "kmcb200_background_potential": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _pi, _i, _d, _d, _d, _vp, _pi]),
+    "kmcb200_comm_create": (_i, [_vp, _i, _i, _i, _pi, _pi, _pvp]),
+    "kmcb200_comm_destroy": (_i, [_vp]),
+    "kmcb200_comm_ipc_handle": (_i, [_vp, _vp]),
+    "kmcb200_comm_open_peers": (_i, [_vp, _vp]),
+    "kmcb200_kmat_attach_comm": (_i, [_vp, _vp]),
+    "kmcb200_kmat_need_map": (_i, [_vp, _vp]),
+    "kmcb200_comm_set_send_masks": (_i, [_vp, _vp]),
+    "kmcb200_comm_info": (_i, [_vp, _pi, _pi, C.POINTER(C.c_uint), _pll]),
     "kmcb200_poisson_gridless": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _d, _d, _d, _i, _i, _vp]),
     "kmcb200_poisson_stats": (_i, [_vp, _pll, _pll]),
     "kmcb200_sum_potential": (_i, [_vp, _i, _vp, _vp]),

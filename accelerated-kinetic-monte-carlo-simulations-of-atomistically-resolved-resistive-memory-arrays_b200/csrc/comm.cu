@@ -1,0 +1,209 @@
+// comm.cu -- exchange plan of the row-sharded solver (see comm.cuh): arena allocation, CUDA-IPC peer mapping, halo
+// need map / send masks.  Bootstrap data (64-byte IPC handles, need maps) is moved between the processes by the
+// caller (torch.distributed in this repo's Python mirror, any out-of-band channel in a C++ host).
+#include "comm.cuh"
+#include "kmat.cuh"
+
+namespace {
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+__global__ void need_map_kernel(int rows, const int *__restrict__ row_ptr, const int *__restrict__ col, int own_lo,
+                                int own_hi, unsigned char *__restrict__ need) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    for (int k = row_ptr[r]; k < row_ptr[r + 1]; ++k) {
+        int j = col[k];
+        if (j < own_lo || j >= own_hi) need[j] = 1;
+    }
+}
+
+// all_need: size x n_global bytes (row q = need map of rank q).  send_mask[i] bit q <=> rank q needs my row i.
+__global__ void send_mask_kernel(int rows, int row_start, int n_global, int size, int rank,
+                                 const unsigned char *__restrict__ all_need, unsigned char *__restrict__ send_mask) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    unsigned m = 0;
+    for (int q = 0; q < size; ++q)
+        if (q != rank && all_need[(size_t)q * n_global + row_start + i]) m |= 1u << q;
+    send_mask[i] = (unsigned char)m;
+}
+
+__global__ void recv_mask_kernel(int n_global, const unsigned char *__restrict__ my_need, const int *__restrict__ displs,
+                                 int size, unsigned *__restrict__ mask_out) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_global || !my_need[j]) return;
+    int q = 0;
+    while (q + 1 < size && j >= displs[q + 1]) ++q;
+    atomicOr(mask_out, 1u << q);
+}
+
+int comm_alloc(kmcb200_comm *c) {
+    const size_t n = (size_t)c->n_global;
+    size_t off = 0;
+    c->off_p[0] = off; off = align_up(off + n * sizeof(double), 256);
+    c->off_p[1] = off; off = align_up(off + n * sizeof(double), 256);
+    c->off_partials = off; off = align_up(off + (size_t)KMC_DOT_SLOTS * c->nchunks_global * sizeof(double), 256);
+    c->off_flag_dot = off; off += 256;
+    c->off_flag_halo = off; off += 256;
+    c->arena_bytes = align_up(off, 2 << 20);
+    KMC_CUDA(cudaMalloc((void **)&c->arena, c->arena_bytes));
+    KMC_CUDA(cudaMemsetAsync(c->arena, 0, c->arena_bytes, c->ctx->stream));
+    KMC_CUDA(cudaMalloc((void **)&c->send_mask, (size_t)c->counts[c->rank] + 1));
+    KMC_CUDA(cudaMemsetAsync(c->send_mask, 0, (size_t)c->counts[c->rank] + 1, c->ctx->stream));
+    KMC_CUDA(cudaStreamSynchronize(c->ctx->stream));
+    c->peer_arena[c->rank] = c->arena;
+    return 0;
+}
+
+}  // namespace
+
+void kmc_comm_fill_dev(kmcb200_comm *c) {
+    CommDev &d = c->dev;
+    d.rank = c->rank;
+    d.size = c->size;
+    d.row_start = c->displs[c->rank];
+    d.n_global = c->n_global;
+    d.nchunks_global = c->nchunks_global;
+    d.chunk_start = d.row_start / KMCB200_CHUNK;
+    d.recv_mask = c->recv_mask;
+    d.p_full[0] = (double *)(c->arena + c->off_p[0]);
+    d.p_full[1] = (double *)(c->arena + c->off_p[1]);
+    d.partials = (double *)(c->arena + c->off_partials);
+    d.flag_dot = (unsigned long long *)(c->arena + c->off_flag_dot);
+    d.flag_halo = (unsigned long long *)(c->arena + c->off_flag_halo);
+    for (int q = 0; q < KMC_MAX_RANKS; ++q) {
+        char *base = (q < c->size) ? c->peer_arena[q] : nullptr;
+        d.peer_p_full[q][0] = base ? (double *)(base + c->off_p[0]) : nullptr;
+        d.peer_p_full[q][1] = base ? (double *)(base + c->off_p[1]) : nullptr;
+        d.peer_partials[q] = base ? (double *)(base + c->off_partials) : nullptr;
+        d.peer_flag_dot[q] = base ? (unsigned long long *)(base + c->off_flag_dot) : nullptr;
+        d.peer_flag_halo[q] = base ? (unsigned long long *)(base + c->off_flag_halo) : nullptr;
+    }
+    d.send_mask = c->send_mask;
+}
+
+int kmc_comm_create_local(kmcb200_ctx *ctx, int n_rows, kmcb200_comm **out) {
+    int counts[1] = {n_rows}, displs[1] = {0};
+    return kmcb200_comm_create(ctx, 0, 1, n_rows, counts, displs, out);
+}
+
+extern "C" int kmcb200_comm_create(kmcb200_ctx *ctx, int rank, int size, int n_global_rows, const int *counts,
+                                   const int *displs, kmcb200_comm **comm_out) {
+    KMC_CHECK_ARG(ctx && counts && displs && comm_out, "null pointer");
+    KMC_CHECK_ARG(size >= 1 && size <= KMC_MAX_RANKS && rank >= 0 && rank < size, "rank/size (<= 8 ranks)");
+    long long sum = 0;
+    for (int q = 0; q < size; ++q) {
+        KMC_CHECK_ARG(displs[q] == sum, "displs must be the prefix sums of counts");
+        KMC_CHECK_ARG(size == 1 || displs[q] % KMCB200_CHUNK == 0 || counts[q] == 0,
+                      "rank boundaries must be multiples of 256 rows (kmcb200_partition_aligned)");
+        sum += counts[q];
+    }
+    KMC_CHECK_ARG(sum == n_global_rows, "counts do not add up to n_global_rows");
+    kmcb200_comm *c = new kmcb200_comm();
+    c->ctx = ctx;
+    c->rank = rank;
+    c->size = size;
+    c->n_global = n_global_rows;
+    c->nchunks_global = (n_global_rows + KMCB200_CHUNK - 1) / KMCB200_CHUNK;
+    c->counts.assign(counts, counts + size);
+    c->displs.assign(displs, displs + size);
+    int rc = comm_alloc(c);
+    if (rc) { delete c; return rc; }
+    c->peers_open = (size == 1);
+    kmc_comm_fill_dev(c);
+    *comm_out = c;
+    return 0;
+}
+
+extern "C" int kmcb200_comm_destroy(kmcb200_comm *c) {
+    if (!c) return 0;
+    cudaStreamSynchronize(c->ctx->stream);
+    for (int q = 0; q < c->size; ++q)
+        if (q != c->rank && c->peer_arena[q]) cudaIpcCloseMemHandle(c->peer_arena[q]);
+    cudaFree(c->arena);
+    cudaFree(c->send_mask);
+    delete c;
+    return 0;
+}
+
+extern "C" int kmcb200_comm_ipc_handle(kmcb200_comm *c, void *handle64_host) {
+    KMC_CHECK_ARG(c && handle64_host, "null pointer");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    KMC_CUDA(cudaIpcGetMemHandle(&h, c->arena));
+    memcpy(handle64_host, &h, 64);
+    return 0;
+}
+
+extern "C" int kmcb200_comm_open_peers(kmcb200_comm *c, const void *handles_host) {
+    KMC_CHECK_ARG(c && handles_host, "null pointer");
+    for (int q = 0; q < c->size; ++q) {
+        if (q == c->rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char *)handles_host + 64 * q, 64);
+        void *p = nullptr;
+        KMC_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        c->peer_arena[q] = (char *)p;
+    }
+    c->peers_open = true;
+    kmc_comm_fill_dev(c);
+    return 0;
+}
+
+extern "C" int kmcb200_kmat_attach_comm(kmcb200_kmat *K, kmcb200_comm *c) {
+    KMC_CHECK_ARG(K && c, "null pointer");
+    KMC_CHECK_ARG(K->rows == c->counts[c->rank] && K->row_start == c->displs[c->rank] && K->cols_global == c->n_global,
+                  "matrix rows do not match the communicator's partition");
+    if (K->comm && K->owns_comm) kmcb200_comm_destroy(K->comm);
+    K->comm = c;
+    K->owns_comm = false;
+    return 0;
+}
+
+extern "C" int kmcb200_kmat_need_map(kmcb200_kmat *K, unsigned char *need_dev) {
+    KMC_CHECK_ARG(K && need_dev, "null pointer");
+    kmcb200_ctx *ctx = K->ctx;
+    KMC_CUDA(cudaMemsetAsync(need_dev, 0, (size_t)K->cols_global, ctx->stream));
+    kmc_count_launch();
+    need_map_kernel<<<(K->rows + 127) / 128, 128, 0, ctx->stream>>>(K->rows, K->row_ptr, K->col, K->row_start,
+                                                                   K->row_start + K->rows, need_dev);
+    KMC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int kmcb200_comm_set_send_masks(kmcb200_comm *c, const unsigned char *all_need_dev) {
+    KMC_CHECK_ARG(c && all_need_dev, "null pointer");
+    kmcb200_ctx *ctx = c->ctx;
+    const int rows = c->counts[c->rank];
+    unsigned *d_mask = nullptr;
+    int *d_displs = nullptr;
+    KMC_TRY(kmc_scratch(ctx, 5, 256, (void **)&d_mask));
+    d_displs = (int *)(d_mask + 8);
+    KMC_CUDA(cudaMemsetAsync(d_mask, 0, 32, ctx->stream));
+    KMC_CUDA(cudaMemcpyAsync(d_displs, c->displs.data(), c->size * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    if (rows > 0) {
+        kmc_count_launch();
+        send_mask_kernel<<<(rows + 255) / 256, 256, 0, ctx->stream>>>(rows, c->displs[c->rank], c->n_global, c->size, c->rank,
+                                                                    all_need_dev, c->send_mask);
+    }
+    kmc_count_launch();
+    recv_mask_kernel<<<(c->n_global + 255) / 256, 256, 0, ctx->stream>>>(c->n_global, all_need_dev + (size_t)c->rank * c->n_global,
+                                                                        d_displs, c->size, d_mask);
+    KMC_CUDA(cudaGetLastError());
+    unsigned m = 0;
+    KMC_CUDA(cudaMemcpyAsync(&m, d_mask, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+    KMC_CUDA(cudaStreamSynchronize(ctx->stream));
+    c->recv_mask = m & ~(1u << c->rank);
+    kmc_comm_fill_dev(c);
+    return 0;
+}
+
+extern "C" int kmcb200_comm_info(kmcb200_comm *c, int *rank, int *size, unsigned *recv_mask, long long *arena_bytes) {
+    KMC_CHECK_ARG(c != nullptr, "comm");
+    if (rank) *rank = c->rank;
+    if (size) *size = c->size;
+    if (recv_mask) *recv_mask = c->recv_mask;
+    if (arena_bytes) *arena_bytes = (long long)c->arena_bytes;
+    return 0;
+}

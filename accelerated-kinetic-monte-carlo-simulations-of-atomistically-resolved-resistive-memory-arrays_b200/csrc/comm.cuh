@@ -1,0 +1,72 @@
+// comm.cuh -- row-sharded solver exchange over NVLink peer memory (one process per GPU).
+//
+// Replaces the reference's GPU-aware MPI traffic inside the PCG: the pack -> MPI_Isend/Irecv -> unpack halo exchange of
+// dspmv::gpu_packing_cam (dist_iterative/dist_spmv_gpu_packing.cpp:106-228) and the MPI_Allreduce after every hipblasDdot
+// (dist_iterative/dist_conjugate_gradient.cpp:188,213,241,265).  Here the kernel that PRODUCES a value also delivers it:
+//   * the p-update kernel stores each new p entry into its own p vector and, for rows a peer's matrix block
+//     references, directly into that peer's p vector (remote NVLink stores), then raises a flag;
+//   * every dot-producing kernel stores its 256-row chunk partials into all peers' partial arrays; the last CTA of
+//     each rank waits for the peers' flags and reduces ALL partials in the fixed order of the summation spec, so every
+//     rank holds the bit-identical scalar without a collective call or a host round trip.
+// With size == 1 the same kernels run with empty peer loops (this is the single-GPU path).
+#pragma once
+#include "common.cuh"
+
+#define KMC_MAX_RANKS 8
+#define KMC_DOT_SLOTS 5  // 0: p.Ap, 1: r.z, 2: b.b, 3: r.z (setup), 4: kmcb200_dot
+
+// by-value kernel argument
+struct CommDev {
+    int rank, size;
+    int row_start;            // first owned global row (multiple of 256 when size > 1)
+    int n_global;             // global number of rows
+    int nchunks_global;       // ceil(n_global / 256)
+    int chunk_start;          // row_start / 256
+    unsigned recv_mask;       // peers this rank's matrix rows read p entries from
+    double *p_full[2];        // local, double buffered, indexed by global row
+    double *partials;         // local, KMC_DOT_SLOTS * nchunks_global
+    unsigned long long *flag_dot;   // local, [KMC_MAX_RANKS] written by peers
+    unsigned long long *flag_halo;  // local, [KMC_MAX_RANKS] written by peers
+    double *peer_p_full[KMC_MAX_RANKS][2];
+    double *peer_partials[KMC_MAX_RANKS];
+    unsigned long long *peer_flag_dot[KMC_MAX_RANKS];   // peer's flag_dot array (we write entry [rank])
+    unsigned long long *peer_flag_halo[KMC_MAX_RANKS];
+    const unsigned char *send_mask;  // local rows: bit q set -> peer q needs this row's p entry
+};
+
+struct kmcb200_comm {
+    kmcb200_ctx *ctx = nullptr;
+    int rank = 0, size = 1;
+    int n_global = 0, nchunks_global = 0;
+    std::vector<int> counts, displs;
+    char *arena = nullptr;  // local allocation shared with the peers through CUDA IPC
+    size_t arena_bytes = 0;
+    size_t off_p[2] = {0, 0}, off_partials = 0, off_flag_dot = 0, off_flag_halo = 0;
+    char *peer_arena[KMC_MAX_RANKS] = {nullptr};
+    bool peers_open = false;
+    unsigned char *send_mask = nullptr;  // counts[rank] bytes
+    unsigned recv_mask = 0;
+    unsigned long long dot_seq = 0, halo_seq = 0;  // host-side launch counters (identical on every rank)
+    CommDev dev;
+};
+
+int kmc_comm_create_local(kmcb200_ctx *ctx, int n_rows, kmcb200_comm **out);  // size == 1
+void kmc_comm_fill_dev(kmcb200_comm *c);
+
+// ---- device side --------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void kmc_store_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long kmc_load_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// one thread waits until every peer in `mask` has published sequence number >= seq
+__device__ __forceinline__ void kmc_wait_flags(const unsigned long long *flags, unsigned mask, int self,
+                                               unsigned long long seq) {
+    for (int q = 0; q < KMC_MAX_RANKS; ++q) {
+        if (q == self || !((mask >> q) & 1u)) continue;
+        while (kmc_load_acquire_sys(flags + q) < seq) { __nanosleep(20); }
+    }
+}

@@ -5,6 +5,7 @@
 // values, diagonal, inverse diagonal and rhs in a single pass over the CSR (coalesced col reads / val writes).
 #include <stdlib.h>
 
+#include "comm.cuh"
 #include "kmat.cuh"
 
 namespace {
@@ -96,10 +97,12 @@ __global__ void __launch_bounds__(256) assemble_kernel(int rows, int row_start, 
 }  // namespace
 
 int kmc_kmat_finalize(kmcb200_kmat *K) {
-    KMC_CUDA(cudaMalloc(&K->p_full, (size_t)K->cols_global * sizeof(double)));
     KMC_CUDA(cudaMalloc(&K->Ap, (size_t)K->rows * sizeof(double)));
     KMC_CUDA(cudaMalloc(&K->z, (size_t)K->rows * sizeof(double)));
-    KMC_CUDA(cudaMemsetAsync(K->p_full, 0, (size_t)K->cols_global * sizeof(double), K->ctx->stream));
+    if (K->rows == K->cols_global) {  // single rank: private exchange plan with empty peer loops
+        KMC_TRY(kmc_comm_create_local(K->ctx, K->rows, &K->comm));
+        K->owns_comm = true;
+    }
     K->plan_max_unique = 0;
     if (getenv("KMCB200_SPMV_STAGED")) return kmc_build_spmv_plan(K);  // opt-in experiment, see pcg.cu
     return 0;
@@ -137,7 +140,8 @@ extern "C" int kmcb200_kmat_destroy(kmcb200_kmat *K) {
         cudaFree(K->left_row_ptr); cudaFree(K->left_col); cudaFree(K->right_row_ptr); cudaFree(K->right_col);
         cudaFree(K->inv_diag); cudaFree(K->rhs);
     }
-    cudaFree(K->p_full); cudaFree(K->Ap); cudaFree(K->z); cudaFree(K->site_class);
+    if (K->comm && K->owns_comm) kmcb200_comm_destroy(K->comm);
+    cudaFree(K->Ap); cudaFree(K->z); cudaFree(K->site_class);
     cudaFree(K->u_ptr); cudaFree(K->u_col); cudaFree(K->lcol);
     delete K;
     return 0;

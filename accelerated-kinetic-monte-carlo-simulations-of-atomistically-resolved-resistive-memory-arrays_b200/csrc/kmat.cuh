@@ -19,10 +19,11 @@ struct kmcb200_kmat {
     int *left_row_ptr = nullptr, *left_col = nullptr, *right_row_ptr = nullptr, *right_col = nullptr;
     double *inv_diag = nullptr, *rhs = nullptr;
     // PCG workspace (persistent): p is indexed by GLOBAL interior row (halo entries land in place)
-    double *p_full = nullptr, *Ap = nullptr, *z = nullptr;
+    double *Ap = nullptr, *z = nullptr;  // (the global-indexed p vectors live in the exchange arena, comm.cuh)
     unsigned char *site_class = nullptr;  // N bytes, (re)built by assemble
     size_t site_class_cap = 0;
-    kmcb200_comm *comm = nullptr;  // nullptr: single GPU
+    kmcb200_comm *comm = nullptr;  // exchange plan; a private size-1 plan unless kmcb200_kmat_attach_comm was called
+    bool owns_comm = false;
     // SpMV plan (spmv_plan.cu): per 256-row chunk the sorted unique columns it touches (u_col, CSR-like u_ptr) and a
     // 16-bit chunk-local column id per non-zero (lcol).  The SpMV stages x[u_col] in shared memory once per chunk and
     // gathers from there; HBM traffic per non-zero drops from 12 B (val + int32 col) to 10 B (val + uint16 lcol).

@@ -1,19 +1,20 @@
-// pcg.cu -- a7: CSR SpMV with the p.Ap dot fused into its epilogue, fused Jacobi-PCG vector passes, and the
-// deterministic dot product of the summation spec.
+// pcg.cu -- a7: CSR SpMV with the p.Ap dot fused into its epilogue, fused Jacobi-PCG vector passes, the deterministic
+// dot product of the summation spec, and their row-sharded multi-GPU form (comm.cuh).
 // Reference: dist_iterative/dist_conjugate_gradient.cpp:149-276 (update order kept exactly),
-// dist_iterative/dist_spmv_gpu_packing.cpp:106-228 (SpMV), dist_iterative/utils_cg.cu:323-371 (elementwise).
-// The reference runs per iteration: 1 rocsparse_spmv per neighbour block, 2 hipblasDdot (each a blocking host
-// round trip + MPI_Allreduce), 3 daxpy, 1 dscal, 1 elementwise = 11 vector streams*... Here: 3 kernels per
-// iteration, all scalars stay on the device, 11 vector streams + the matrix (B_iter = 12 nnz + 108 n bytes).
+// dist_iterative/dist_spmv_gpu_packing.cpp:106-228 (SpMV + halo), dist_iterative/utils_cg.cu:323-371 (elementwise).
+// The reference runs per iteration: one rocsparse_spmv per neighbour block with pack/Isend/Irecv/unpack, 2 hipblasDdot
+// (each a blocking host round trip + MPI_Allreduce), 3 daxpy, 1 dscal, 1 elementwise.  Here: 3 kernels per iteration,
+// all scalars stay on the device, halo entries and dot partials are delivered to the peers by the producing kernels.
 #include <stdlib.h>
 #include <string.h>
 
+#include "comm.cuh"
 #include "kmat.cuh"
 
 struct CgState {
     double bb, rz, rz_old, pAp, tol2, scalar_out;
     int k, max_it, done, iters;
-    unsigned cnt[4];
+    unsigned cnt[8];
 };
 
 namespace {
@@ -21,16 +22,48 @@ namespace {
 constexpr int CH = KMCB200_CHUNK;  // 256 rows per CTA == dot chunk
 
 // "last CTA done" election (threadFenceReduction pattern).  Returns true in every thread of the last CTA.
-__device__ __forceinline__ bool last_cta(unsigned *counter, int *sm_flag) {
+// multi: the fence must order this CTA's REMOTE stores too.
+__device__ __forceinline__ bool last_cta(unsigned *counter, int *sm_flag, bool multi) {
     if (threadIdx.x == 0) {
-        __threadfence();
+        if (multi) __threadfence_system(); else __threadfence();
         unsigned t = atomicAdd(counter, 1u);
         *sm_flag = (t == gridDim.x - 1);
     }
     __syncthreads();
     bool last = (*sm_flag != 0);
-    if (last) __threadfence();
+    if (last) {
+        if (multi) __threadfence_system(); else __threadfence();
+    }
     return last;
+}
+
+// publish this CTA's chunk partial(s) locally and to every peer (thread 0)
+__device__ __forceinline__ void publish_partial(const CommDev &cm, int slot, double v) {
+    const size_t idx = (size_t)slot * cm.nchunks_global + cm.chunk_start + blockIdx.x;
+    cm.partials[idx] = v;
+    for (int q = 0; q < cm.size; ++q)
+        if (q != cm.rank) cm.peer_partials[q][idx] = v;
+}
+// last CTA: tell the peers our partials are in place, wait for theirs (all threads return after the wait)
+__device__ __forceinline__ void exchange_partials(const CommDev &cm, unsigned long long seq) {
+    if (cm.size > 1) {
+        if (threadIdx.x == 0) {
+            for (int q = 0; q < cm.size; ++q)
+                if (q != cm.rank) kmc_store_release_sys(cm.peer_flag_dot[q] + cm.rank, seq);
+            kmc_wait_flags(cm.flag_dot, (1u << cm.size) - 1u, cm.rank, seq);
+            __threadfence_system();
+        }
+        __syncthreads();
+    }
+}
+__device__ __forceinline__ void wait_halo(const CommDev &cm, unsigned long long seq) {
+    if (cm.recv_mask) {  // uniform
+        if (threadIdx.x == 0) {
+            kmc_wait_flags(cm.flag_halo, cm.recv_mask, cm.rank, seq);
+            __threadfence_system();
+        }
+        __syncthreads();
+    }
 }
 
 // y = A x (x indexed by GLOBAL column), optional fused partial of  x[row].y[row]  (p.Ap)
@@ -39,13 +72,14 @@ __device__ __forceinline__ bool last_cta(unsigned *counter, int *sm_flag) {
 template <int L, bool DOT>
 __global__ void __launch_bounds__(CH) spmv_kernel(int rows, const int *__restrict__ row_ptr,
                                                  const int *__restrict__ col, const double *__restrict__ val,
-                                                 const double *__restrict__ xg, int row_start,
-                                                 double *__restrict__ y, double *__restrict__ partials,
+                                                 const double *__restrict__ xg, double *__restrict__ y, CommDev cm,
+                                                 unsigned long long halo_seq, unsigned long long dot_seq,
                                                  CgState *__restrict__ st) {
     if (DOT && st->done) return;
     __shared__ double prod[CH];
     __shared__ double red[8];
     __shared__ int flag;
+    wait_halo(cm, halo_seq);
     constexpr int GROUPS = CH / L;  // rows per pass
     const int lane = threadIdx.x % L;
     const int grp = threadIdx.x / L;
@@ -83,7 +117,7 @@ __global__ void __launch_bounds__(CH) spmv_kernel(int rows, const int *__restric
             double pv = 0.0;
             if (r < rows) {
                 y[r] = acc;
-                if (DOT) pv = xg[row_start + r] * acc;
+                if (DOT) pv = xg[cm.row_start + r] * acc;
             }
             if (DOT) prod[rl] = pv;
         }
@@ -91,9 +125,10 @@ __global__ void __launch_bounds__(CH) spmv_kernel(int rows, const int *__restric
     if (DOT) {
         __syncthreads();
         double c = kmc_chunk_reduce_256(prod[threadIdx.x], red);
-        if (threadIdx.x == 0) partials[blockIdx.x] = c;
-        if (last_cta(&st->cnt[0], &flag)) {
-            double tot = kmc_final_reduce(partials, gridDim.x, red);
+        if (threadIdx.x == 0) publish_partial(cm, 0, c);
+        if (last_cta(&st->cnt[0], &flag, cm.size > 1)) {
+            exchange_partials(cm, dot_seq);
+            double tot = kmc_final_reduce(cm.partials, cm.nchunks_global, red);
             if (threadIdx.x == 0) {
                 st->pAp = tot;
                 st->cnt[0] = 0;
@@ -102,16 +137,15 @@ __global__ void __launch_bounds__(CH) spmv_kernel(int rows, const int *__restric
     }
 }
 
-// Shared-memory staged variant: the chunk's unique columns (u_col) are gathered ONCE into shared memory, every
-// non-zero then reads x through its 16-bit chunk-local id.  Same row reduction spec (bit-identical results).
+// Shared-memory staged variant (single GPU, opt-in): the chunk's unique columns (u_col) are gathered ONCE into shared
+// memory, every non-zero then reads x through its 16-bit chunk-local id.  Same row reduction spec.
 template <int L, bool DOT>
 __global__ void __launch_bounds__(CH) spmv_staged_kernel(int rows, const int *__restrict__ row_ptr,
                                                         const unsigned short *__restrict__ lcol,
                                                         const double *__restrict__ val,
                                                         const int *__restrict__ u_ptr, const int *__restrict__ u_col,
-                                                        const double *__restrict__ xg, int row_start,
-                                                        double *__restrict__ y, double *__restrict__ partials,
-                                                        CgState *__restrict__ st) {
+                                                        const double *__restrict__ xg, double *__restrict__ y,
+                                                        CommDev cm, CgState *__restrict__ st) {
     if (DOT && st->done) return;
     extern __shared__ double xs[];  // the chunk's x window
     __shared__ double prod[CH];
@@ -155,7 +189,7 @@ __global__ void __launch_bounds__(CH) spmv_staged_kernel(int rows, const int *__
             double pv = 0.0;
             if (r < rows) {
                 y[r] = acc;
-                if (DOT) pv = xg[row_start + r] * acc;
+                if (DOT) pv = xg[cm.row_start + r] * acc;
             }
             if (DOT) prod[rl] = pv;
         }
@@ -163,9 +197,9 @@ __global__ void __launch_bounds__(CH) spmv_staged_kernel(int rows, const int *__
     if (DOT) {
         __syncthreads();
         double c = kmc_chunk_reduce_256(prod[threadIdx.x], red);
-        if (threadIdx.x == 0) partials[blockIdx.x] = c;
-        if (last_cta(&st->cnt[0], &flag)) {
-            double tot = kmc_final_reduce(partials, gridDim.x, red);
+        if (threadIdx.x == 0) publish_partial(cm, 0, c);
+        if (last_cta(&st->cnt[0], &flag, false)) {
+            double tot = kmc_final_reduce(cm.partials, cm.nchunks_global, red);
             if (threadIdx.x == 0) {
                 st->pAp = tot;
                 st->cnt[0] = 0;
@@ -176,8 +210,8 @@ __global__ void __launch_bounds__(CH) spmv_staged_kernel(int rows, const int *__
 
 // r = b - A x0 ; z = M^-1 r ; bb = b.b ; rz = r.z     (dist_conjugate_gradient.cpp:187-213)
 __global__ void __launch_bounds__(CH) cg_init_kernel(int rows, double *__restrict__ r, const double *__restrict__ Ap,
-                                                    const double *__restrict__ dinv, double *__restrict__ z,
-                                                    double *__restrict__ partials, CgState *__restrict__ st) {
+                                                    const double *__restrict__ dinv, double *__restrict__ z, CommDev cm,
+                                                    unsigned long long dot_seq, CgState *__restrict__ st) {
     __shared__ double red[8];
     __shared__ int flag;
     int i = blockIdx.x * CH + threadIdx.x;
@@ -194,12 +228,13 @@ __global__ void __launch_bounds__(CH) cg_init_kernel(int rows, double *__restric
     double cbb = kmc_chunk_reduce_256(vbb, red);
     double crz = kmc_chunk_reduce_256(vrz, red);
     if (threadIdx.x == 0) {
-        partials[blockIdx.x] = cbb;
-        partials[gridDim.x + blockIdx.x] = crz;
+        publish_partial(cm, 2, cbb);
+        publish_partial(cm, 3, crz);
     }
-    if (last_cta(&st->cnt[1], &flag)) {
-        double bb = kmc_final_reduce(partials, gridDim.x, red);
-        double rz = kmc_final_reduce(partials + gridDim.x, gridDim.x, red);
+    if (last_cta(&st->cnt[1], &flag, cm.size > 1)) {
+        exchange_partials(cm, dot_seq);
+        double bb = kmc_final_reduce(cm.partials + (size_t)2 * cm.nchunks_global, cm.nchunks_global, red);
+        double rz = kmc_final_reduce(cm.partials + (size_t)3 * cm.nchunks_global, cm.nchunks_global, red);
         if (threadIdx.x == 0) {
             st->bb = bb;
             st->rz = rz;
@@ -212,27 +247,53 @@ __global__ void __launch_bounds__(CH) cg_init_kernel(int rows, double *__restric
     }
 }
 
-// p = z (k == 1)  or  p = z + (rz/rz_old) p      (dist_conjugate_gradient.cpp:218-227)
-__global__ void __launch_bounds__(256) cg_pupdate_kernel(int rows, int row_start, const double *__restrict__ z,
-                                                        double *__restrict__ p_full, const CgState *__restrict__ st) {
-    if (st->done) return;
+// MODE 1: p = z (k == 1)  or  p = z + (rz/rz_old) p      (dist_conjugate_gradient.cpp:218-227)
+// MODE 0: p = src (the copy of x0 at :178)
+// The new entries are written to this rank's p vector and, for rows a peer's block references, into the peer's.
+template <int MODE>
+__global__ void __launch_bounds__(256) cg_pupdate_kernel(int rows, const double *__restrict__ src,
+                                                        const double *__restrict__ p_old, double *__restrict__ p_new,
+                                                        CommDev cm, int buf, unsigned long long halo_seq,
+                                                        CgState *__restrict__ st) {
+    if (MODE == 1 && st->done) return;
+    __shared__ int flag;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= rows) return;
-    double *p = p_full + row_start;
-    if (st->k == 1) {
-        p[i] = z[i];
-    } else {
-        double b = st->rz / st->rz_old;
-        double t = b * p[i];
-        p[i] = z[i] + t;
+    if (i < rows) {
+        const int g = cm.row_start + i;
+        double v;
+        if (MODE == 0 || st->k == 1) {
+            v = src[i];
+        } else {
+            double b = st->rz / st->rz_old;
+            double t = b * p_old[g];
+            v = src[i] + t;
+        }
+        p_new[g] = v;
+        if (cm.size > 1) {
+            unsigned m = cm.send_mask[i];
+            while (m) {
+                int q = __ffs(m) - 1;
+                m &= m - 1;
+                cm.peer_p_full[q][buf][g] = v;
+            }
+        }
+    }
+    if (cm.size > 1) {
+        if (last_cta(&st->cnt[4], &flag, true)) {
+            if (threadIdx.x == 0) {
+                for (int q = 0; q < cm.size; ++q)
+                    if (q != cm.rank) kmc_store_release_sys(cm.peer_flag_halo[q] + cm.rank, halo_seq);
+                st->cnt[4] = 0;
+            }
+        }
     }
 }
 
 // a = rz / p.Ap ; x += a p ; r -= a Ap ; z = M^-1 r ; rz' = r.z ; k++   (dist_conjugate_gradient.cpp:243-266)
-__global__ void __launch_bounds__(CH) cg_update_kernel(int rows, int row_start, const double *__restrict__ p_full,
+__global__ void __launch_bounds__(CH) cg_update_kernel(int rows, const double *__restrict__ p_full,
                                                       const double *__restrict__ Ap, const double *__restrict__ dinv,
                                                       double *__restrict__ x, double *__restrict__ r,
-                                                      double *__restrict__ z, double *__restrict__ partials,
+                                                      double *__restrict__ z, CommDev cm, unsigned long long dot_seq,
                                                       CgState *__restrict__ st) {
     if (st->done) return;
     __shared__ double red[8];
@@ -242,7 +303,7 @@ __global__ void __launch_bounds__(CH) cg_update_kernel(int rows, int row_start, 
     int i = blockIdx.x * CH + threadIdx.x;
     double v = 0.0;
     if (i < rows) {
-        double pi = p_full[row_start + i];
+        double pi = p_full[cm.row_start + i];
         double xi = fma(a, pi, x[i]);
         double ri = fma(na, Ap[i], r[i]);
         double zi = ri * dinv[i];
@@ -252,9 +313,10 @@ __global__ void __launch_bounds__(CH) cg_update_kernel(int rows, int row_start, 
         v = ri * zi;
     }
     double c = kmc_chunk_reduce_256(v, red);
-    if (threadIdx.x == 0) partials[blockIdx.x] = c;
-    if (last_cta(&st->cnt[2], &flag)) {
-        double rz = kmc_final_reduce(partials, gridDim.x, red);
+    if (threadIdx.x == 0) publish_partial(cm, 1, c);
+    if (last_cta(&st->cnt[2], &flag, cm.size > 1)) {
+        exchange_partials(cm, dot_seq);
+        double rz = kmc_final_reduce(cm.partials + (size_t)cm.nchunks_global, cm.nchunks_global, red);
         if (threadIdx.x == 0) {
             st->rz_old = st->rz;
             st->rz = rz;
@@ -275,7 +337,7 @@ __global__ void __launch_bounds__(CH) dot_kernel(long long n, const double *__re
     double p = (i < n) ? u[i] * v[i] : 0.0;
     double c = kmc_chunk_reduce_256(p, red);
     if (threadIdx.x == 0) partials[blockIdx.x] = c;
-    if (last_cta(&st->cnt[3], &flag)) {
+    if (last_cta(&st->cnt[3], &flag, false)) {
         double tot = kmc_final_reduce(partials, gridDim.x, red);
         if (threadIdx.x == 0) {
             st->scalar_out = tot;
@@ -303,14 +365,18 @@ int ensure_cg_workspace(kmcb200_ctx *ctx, long long nchunks) {
 
 }  // namespace
 
-int kmc_spmv_launch(kmcb200_ctx *ctx, kmcb200_kmat *K, const double *xg, double *y, bool with_dot) {
+// y = A xg for this rank's rows; xg is indexed by global row and must already hold the halo entries (or be awaited
+// through halo_seq).  with_dot: fused p.Ap into CgState::pAp.
+static int spmv_launch(kmcb200_ctx *ctx, kmcb200_kmat *K, const double *xg, double *y, bool with_dot,
+                       unsigned long long halo_seq, unsigned long long dot_seq) {
     constexpr int L = KMCB200_SPMV_LANES;
+    const CommDev &cm = K->comm->dev;
     unsigned blocks = (unsigned)((K->rows + CH - 1) / CH);
     kmc_count_launch();
     const size_t dyn = (size_t)K->plan_max_unique * sizeof(double);
     // The staged kernel only pays off when the rows of a chunk share columns (reuse >> 1); for the DeviceKMC lattices
-    // the measured reuse is 1.3-1.7 and it is SLOWER (371 us vs 197 us at 62 M nnz), so it is opt-in (DESIGN.md 5.3).
-    if (K->plan_max_unique > 0 && dyn <= 200 * 1024) {
+    // the measured reuse is 1.3-1.7 and it is SLOWER (371 us vs 197 us at 62 M nnz), so it is opt-in (DESIGN.md 3).
+    if (K->plan_max_unique > 0 && dyn <= 200 * 1024 && cm.size == 1) {
         static size_t configured = 0;
         if (dyn > configured) {
             KMC_CUDA(cudaFuncSetAttribute(spmv_staged_kernel<L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
@@ -319,33 +385,46 @@ int kmc_spmv_launch(kmcb200_ctx *ctx, kmcb200_kmat *K, const double *xg, double 
         }
         if (with_dot)
             spmv_staged_kernel<L, true><<<blocks, CH, dyn, ctx->stream>>>(K->rows, K->row_ptr, K->lcol, K->val, K->u_ptr,
-                                                                         K->u_col, xg, K->row_start, y, ctx->partials,
-                                                                         ctx->cg_state);
+                                                                         K->u_col, xg, y, cm, ctx->cg_state);
         else
             spmv_staged_kernel<L, false><<<blocks, CH, dyn, ctx->stream>>>(K->rows, K->row_ptr, K->lcol, K->val, K->u_ptr,
-                                                                          K->u_col, xg, K->row_start, y, ctx->partials,
-                                                                          ctx->cg_state);
+                                                                          K->u_col, xg, y, cm, ctx->cg_state);
     } else if (with_dot) {
-        spmv_kernel<L, true><<<blocks, CH, 0, ctx->stream>>>(K->rows, K->row_ptr, K->col, K->val, xg, K->row_start, y,
-                                                            ctx->partials, ctx->cg_state);
+        spmv_kernel<L, true><<<blocks, CH, 0, ctx->stream>>>(K->rows, K->row_ptr, K->col, K->val, xg, y, cm, halo_seq,
+                                                            dot_seq, ctx->cg_state);
     } else {
-        spmv_kernel<L, false><<<blocks, CH, 0, ctx->stream>>>(K->rows, K->row_ptr, K->col, K->val, xg, K->row_start, y,
-                                                             ctx->partials, ctx->cg_state);
+        spmv_kernel<L, false><<<blocks, CH, 0, ctx->stream>>>(K->rows, K->row_ptr, K->col, K->val, xg, y, cm, halo_seq,
+                                                             dot_seq, ctx->cg_state);
     }
     KMC_CUDA(cudaGetLastError());
     return 0;
 }
 
+// copies this rank's x entries into the global-indexed p vector and pushes the halo rows to the peers
+static int push_vector(kmcb200_ctx *ctx, kmcb200_kmat *K, const double *x_local, int *buf_out,
+                       unsigned long long *halo_seq_out) {
+    kmcb200_comm *C = K->comm;
+    const unsigned long long hs = ++C->halo_seq;
+    const int buf = (int)(hs & 1);
+    const unsigned eb = (unsigned)((K->rows + 255) / 256);
+    kmc_count_launch();
+    cg_pupdate_kernel<0><<<eb, 256, 0, ctx->stream>>>(K->rows, x_local, nullptr, C->dev.p_full[buf], C->dev, buf, hs,
+                                                     ctx->cg_state);
+    KMC_CUDA(cudaGetLastError());
+    *buf_out = buf;
+    *halo_seq_out = hs;
+    return 0;
+}
+
 extern "C" int kmcb200_spmv(kmcb200_ctx *ctx, kmcb200_kmat *K, const double *x_local, double *y_local) {
     KMC_CHECK_ARG(ctx && K && x_local && y_local, "null pointer");
-    long long nchunks = (K->rows + CH - 1) / CH;
-    KMC_TRY(ensure_cg_workspace(ctx, nchunks));
-    const double *xg = x_local;
-    if (K->rows != K->cols_global) {
-        kmc_set_error("kmcb200_spmv on a row-sharded matrix needs the multi-GPU exchange (kmcb200_comm_*)");
-        return KMCB200_E_COMM;
-    }
-    return kmc_spmv_launch(ctx, K, xg, y_local, false);
+    KMC_CHECK_ARG(K->comm != nullptr, "kmat has no exchange plan");
+    KMC_TRY(ensure_cg_workspace(ctx, 1));
+    if (K->comm->size == 1) return spmv_launch(ctx, K, x_local, y_local, false, 0, 0);
+    int buf;
+    unsigned long long hs;
+    KMC_TRY(push_vector(ctx, K, x_local, &buf, &hs));
+    return spmv_launch(ctx, K, K->comm->dev.p_full[buf], y_local, false, hs, 0);
 }
 
 extern "C" int kmcb200_dot(kmcb200_ctx *ctx, const double *u, const double *v, long long n, double *result_host) {
@@ -366,8 +445,10 @@ extern "C" int kmcb200_pcg_jacobi(kmcb200_ctx *ctx, kmcb200_kmat *K, double *r_l
                                   const double *diag_inv_local, double relative_tolerance, int max_iterations,
                                   int *iterations_host) {
     KMC_CHECK_ARG(ctx && K && r_local && x_local && diag_inv_local, "null pointer");
-    if (K->rows != K->cols_global) {
-        kmc_set_error("row-sharded PCG needs the multi-GPU exchange (kmcb200_comm_*)");
+    KMC_CHECK_ARG(K->comm != nullptr, "kmat has no exchange plan");
+    kmcb200_comm *C = K->comm;
+    if (C->size > 1 && !C->peers_open) {
+        kmc_set_error("row-sharded PCG: kmcb200_comm_open_peers / kmcb200_comm_set_send_masks were not called");
         return KMCB200_E_COMM;
     }
     const int rows = K->rows;
@@ -382,9 +463,18 @@ extern "C" int kmcb200_pcg_jacobi(kmcb200_ctx *ctx, kmcb200_kmat *K, double *r_l
     h->done = 0;
     KMC_CUDA(cudaMemcpyAsync(st, h, sizeof(CgState), cudaMemcpyHostToDevice, ctx->stream));
     // A*x0 (:191), residual + preconditioned residual + both setup dots (:187-213)
-    KMC_TRY(kmc_spmv_launch(ctx, K, x_local, K->Ap, false));
+    int buf = 0;
+    unsigned long long hs = 0;
+    if (C->size == 1) {
+        KMC_TRY(spmv_launch(ctx, K, x_local, K->Ap, false, 0, 0));
+        hs = C->halo_seq;
+        buf = (int)(hs & 1);
+    } else {
+        KMC_TRY(push_vector(ctx, K, x_local, &buf, &hs));
+        KMC_TRY(spmv_launch(ctx, K, C->dev.p_full[buf], K->Ap, false, hs, 0));
+    }
     kmc_count_launch();
-    cg_init_kernel<<<nchunks, CH, 0, ctx->stream>>>(rows, r_local, K->Ap, diag_inv_local, K->z, ctx->partials, st);
+    cg_init_kernel<<<nchunks, CH, 0, ctx->stream>>>(rows, r_local, K->Ap, diag_inv_local, K->z, C->dev, ++C->dot_seq, st);
     KMC_CUDA(cudaGetLastError());
     int *h_flags = (int *)((char *)ctx->h_mail + 512);
     auto read_flags = [&]() -> int {
@@ -397,12 +487,15 @@ extern "C" int kmcb200_pcg_jacobi(kmcb200_ctx *ctx, kmcb200_kmat *K, double *r_l
     const unsigned eb = (unsigned)((rows + 255) / 256);
     while (!h_flags[2]) {  // done
         for (int b = 0; b < batch; ++b) {
+            const unsigned long long hs2 = ++C->halo_seq;
+            const int nb = (int)(hs2 & 1);
             kmc_count_launch();
-            cg_pupdate_kernel<<<eb, 256, 0, ctx->stream>>>(rows, K->row_start, K->z, K->p_full, st);
-            KMC_TRY(kmc_spmv_launch(ctx, K, K->p_full, K->Ap, true));
+            cg_pupdate_kernel<1><<<eb, 256, 0, ctx->stream>>>(rows, K->z, C->dev.p_full[nb ^ 1], C->dev.p_full[nb], C->dev,
+                                                             nb, hs2, st);
+            KMC_TRY(spmv_launch(ctx, K, C->dev.p_full[nb], K->Ap, true, hs2, ++C->dot_seq));
             kmc_count_launch();
-            cg_update_kernel<<<nchunks, CH, 0, ctx->stream>>>(rows, K->row_start, K->p_full, K->Ap, diag_inv_local,
-                                                             x_local, r_local, K->z, ctx->partials, st);
+            cg_update_kernel<<<nchunks, CH, 0, ctx->stream>>>(rows, C->dev.p_full[nb], K->Ap, diag_inv_local, x_local,
+                                                             r_local, K->z, C->dev, ++C->dot_seq, st);
         }
         KMC_CUDA(cudaGetLastError());
         KMC_TRY(read_flags());

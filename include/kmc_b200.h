@@ -47,6 +47,7 @@ enum { KMCB200_VACANCY_GENERATION = 0, KMCB200_VACANCY_RECOMBINATION = 1, KMCB20
 typedef struct kmcb200_ctx kmcb200_ctx;        /* device + stream + scratch                         */
 typedef struct kmcb200_kmat kmcb200_kmat;      /* K matrix: reference Distributed_matrix + contact CSR */
 typedef struct kmcb200_events kmcb200_events;  /* event list workspace + KMC RNG                     */
+typedef struct kmcb200_comm kmcb200_comm;      /* row-sharded solver exchange plan (peer memory)     */
 
 const char *kmcb200_last_error(void);
 int kmcb200_version(void);
@@ -153,6 +154,27 @@ int kmcb200_background_potential(kmcb200_ctx *ctx, kmcb200_kmat *kmat, int N, in
                                  const int *element, const int *charge, const int *metals_host, int num_metals,
                                  double Vd, double high_G, double low_G, double *site_potential_boundary,
                                  int *iterations_host);
+
+/* ------------------------------------------------------------------------------------------------
+ * (e) Multi-GPU: one process per GPU, interior rows sharded in contiguous blocks whose boundaries are multiples of
+ * 256 (kmcb200_partition_aligned).  Replaces the GPU-aware MPI traffic of the reference's distributed PCG
+ * (dist_iterative/dist_spmv_gpu_packing.cpp:106-228 halo exchange, dist_conjugate_gradient.cpp:188,213,241,265
+ * Allreduce) by remote stores over NVLink peer memory issued by the producing kernels.  Bootstrap:
+ *   1. every rank: kmcb200_comm_create, kmcb200_comm_ipc_handle  -> all-gather the 64-byte handles out of band
+ *   2. every rank: kmcb200_comm_open_peers(all handles)
+ *   3. every rank: kmcb200_initialize_sparsity_K(row_start, row_count of this rank), kmcb200_kmat_attach_comm,
+ *      kmcb200_kmat_need_map -> all-gather the n_global-byte maps out of band -> kmcb200_comm_set_send_masks
+ * afterwards kmcb200_pcg_jacobi / kmcb200_spmv / kmcb200_background_potential work on the sharded matrix and return
+ * bit-identical results on every rank and for every rank count. */
+int kmcb200_comm_create(kmcb200_ctx *ctx, int rank, int size, int n_global_rows, const int *counts_host,
+                        const int *displs_host, kmcb200_comm **comm_out);
+int kmcb200_comm_destroy(kmcb200_comm *comm);
+int kmcb200_comm_ipc_handle(kmcb200_comm *comm, void *handle64_host);
+int kmcb200_comm_open_peers(kmcb200_comm *comm, const void *handles_host /* size * 64 bytes */);
+int kmcb200_kmat_attach_comm(kmcb200_kmat *kmat, kmcb200_comm *comm);
+int kmcb200_kmat_need_map(kmcb200_kmat *kmat, unsigned char *need_dev /* n_global bytes, device */);
+int kmcb200_comm_set_send_masks(kmcb200_comm *comm, const unsigned char *all_need_dev /* size * n_global, device */);
+int kmcb200_comm_info(kmcb200_comm *comm, int *rank, int *size, unsigned *recv_mask, long long *arena_bytes);
 
 /* ------------------------------------------------------------------------------------------------
  * a8.  Replaces poisson_gridless_gpu (src/gpu_solvers.h:173-178, src/potential_solver_gpu.cu:1525-1564,
