@@ -103,6 +103,7 @@ SIGNATURES = {
     "kmcb200_spmv": (_i, [_vp, _vp, _vp, _vp]),
     "kmcb200_dot": (_i, [_vp, _vp, _vp, _ll, _pd]),
     "kmcb200_background_potential": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _pi, _i, _d, _d, _d, _vp, _pi]),
+    "kmcb200_sparsity_K_row_counts": (_i, [_vp, _i, _vp, _vp, _vp, _pd, _i, _d, _i, _i, _vp]),
     "kmcb200_comm_create": (_i, [_vp, _i, _i, _i, _pi, _pi, _pvp]),
     "kmcb200_comm_destroy": (_i, [_vp]),
     "kmcb200_comm_ipc_handle": (_i, [_vp, _vp]),
@@ -340,6 +341,14 @@ class Context:
         _check(self.lib.kmcb200_initialize_sparsity_K(self.h, N, _ptr(x), _ptr(y), _ptr(z), lat, int(pbc), nn_dist,
                                                       N_left, N_right, row_start, row_count, C.byref(h)))
         return KMatrix(self, h)
+
+    def sparsity_K_row_counts(self, x, y, z, lattice, pbc, nn_dist, N_left, N_right):
+        N = x.numel()
+        out = self.empty_i(N - N_left - N_right, 0)
+        lat = (C.c_double * 3)(*[float(v) for v in lattice])
+        _check(self.lib.kmcb200_sparsity_K_row_counts(self.h, N, _ptr(x), _ptr(y), _ptr(z), lat, int(pbc), nn_dist, N_left,
+                                                      N_right, _ptr(out)))
+        return out
 
     def kmat_from_csr(self, row_ptr, col, val, cols_global=None, row_start=0):
         rows = row_ptr.numel() - 1

@@ -359,6 +359,25 @@ extern "C" int kmcb200_initialize_sparsity_K(kmcb200_ctx *ctx, int N, const doub
     return 0;
 }
 
+// Non-zeros per interior row (interior block only) for ALL rows: lets the caller pick nnz-balanced, chunk-aligned rank
+// boundaries before any rank builds its shard (the reference splits by row count only, src/KMC_comm.h:249-263).
+extern "C" int kmcb200_sparsity_K_row_counts(kmcb200_ctx *ctx, int N, const double *x, const double *y, const double *z,
+                                             const double *lattice_host, int pbc, double nn_dist, int N_left,
+                                             int N_right, int *row_nnz_dev) {
+    KMC_CHECK_ARG(ctx && x && y && z && lattice_host && row_nnz_dev, "null pointer");
+    int n_int = N - N_left - N_right;
+    KMC_CHECK_ARG(n_int > 0, "N_left/N_right");
+    CellGridDev g;
+    KMC_TRY(kmc_build_cellgrid(ctx, x, y, z, 0, N, nn_dist, pbc, lattice_host, &g));
+    int *tmp = nullptr;
+    KMC_TRY(kmc_scratch(ctx, 6, (size_t)2 * n_int * sizeof(int), (void **)&tmp));
+    kmc_count_launch();
+    ksparsity_count_kernel<<<(n_int + 127) / 128, 128, 0, ctx->stream>>>(g, x, y, z, N, N_left, N_right, pbc, nn_dist, 0,
+                                                                        n_int, row_nnz_dev, tmp, tmp + n_int);
+    KMC_CUDA(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int kmcb200_kmat_block_view(kmcb200_kmat *K, int col_start, int col_count, int *row_ptr_out, int *col_out,
                                        long long *nnz_host) {
     KMC_CHECK_ARG(K && row_ptr_out && nnz_host, "null pointer");

@@ -22,31 +22,38 @@ namespace {
 constexpr int CH = KMCB200_CHUNK;  // 256 rows per CTA == dot chunk
 
 // "last CTA done" election (threadFenceReduction pattern).  Returns true in every thread of the last CTA.
-// multi: the fence must order this CTA's REMOTE stores too.
-__device__ __forceinline__ bool last_cta(unsigned *counter, int *sm_flag, bool multi) {
+// remote: this CTA issued stores to peer memory that the elected CTA's flag must cover.
+__device__ __forceinline__ bool last_cta(unsigned *counter, int *sm_flag, bool remote) {
     if (threadIdx.x == 0) {
-        if (multi) __threadfence_system(); else __threadfence();
+        if (remote) __threadfence_system(); else __threadfence();
         unsigned t = atomicAdd(counter, 1u);
         *sm_flag = (t == gridDim.x - 1);
     }
     __syncthreads();
     bool last = (*sm_flag != 0);
-    if (last) {
-        if (multi) __threadfence_system(); else __threadfence();
-    }
+    if (last) __threadfence();
     return last;
 }
 
-// publish this CTA's chunk partial(s) locally and to every peer (thread 0)
-__device__ __forceinline__ void publish_partial(const CommDev &cm, int slot, double v) {
-    const size_t idx = (size_t)slot * cm.nchunks_global + cm.chunk_start + blockIdx.x;
-    cm.partials[idx] = v;
-    for (int q = 0; q < cm.size; ++q)
-        if (q != cm.rank) cm.peer_partials[q][idx] = v;
+// chunk partial of global chunk (chunk_start + local_chunk): stored locally; the rank's whole slice is pushed to the
+// peers by the last CTA (exchange_partials), so ordinary CTAs issue no remote traffic and need no system fence
+__device__ __forceinline__ void publish_partial(const CommDev &cm, int slot, int local_chunk, double v) {
+    cm.partials[(size_t)slot * cm.nchunks_global + cm.chunk_start + local_chunk] = v;
 }
-// last CTA: tell the peers our partials are in place, wait for theirs (all threads return after the wait)
-__device__ __forceinline__ void exchange_partials(const CommDev &cm, unsigned long long seq) {
+// last CTA (all threads): copy this rank's partial slice(s) into every peer's array, raise the flag, wait for theirs
+__device__ __forceinline__ void exchange_partials(const CommDev &cm, int slot0, int nslots, int local_chunks,
+                                                  unsigned long long seq) {
     if (cm.size > 1) {
+        for (int sidx = 0; sidx < nslots; ++sidx) {
+            const size_t base = (size_t)(slot0 + sidx) * cm.nchunks_global + cm.chunk_start;
+            for (int i = threadIdx.x; i < local_chunks; i += blockDim.x) {
+                const double v = __ldcg(cm.partials + base + i);
+                for (int q = 0; q < cm.size; ++q)
+                    if (q != cm.rank) cm.peer_partials[q][base + i] = v;
+            }
+        }
+        __threadfence_system();
+        __syncthreads();
         if (threadIdx.x == 0) {
             for (int q = 0; q < cm.size; ++q)
                 if (q != cm.rank) kmc_store_release_sys(cm.peer_flag_dot[q] + cm.rank, seq);
@@ -56,16 +63,6 @@ __device__ __forceinline__ void exchange_partials(const CommDev &cm, unsigned lo
         __syncthreads();
     }
 }
-__device__ __forceinline__ void wait_halo(const CommDev &cm, unsigned long long seq) {
-    if (cm.recv_mask) {  // uniform
-        if (threadIdx.x == 0) {
-            kmc_wait_flags(cm.flag_halo, cm.recv_mask, cm.rank, seq);
-            __threadfence_system();
-        }
-        __syncthreads();
-    }
-}
-
 // y = A x (x indexed by GLOBAL column), optional fused partial of  x[row].y[row]  (p.Ap)
 // Row reduction spec: L lanes per row, lane l accumulates entries l, l+L, ... with fma in increasing k,
 // then a butterfly over the L lanes.
@@ -79,7 +76,6 @@ __global__ void __launch_bounds__(CH) spmv_kernel(int rows, const int *__restric
     __shared__ double prod[CH];
     __shared__ double red[8];
     __shared__ int flag;
-    wait_halo(cm, halo_seq);
     constexpr int GROUPS = CH / L;  // rows per pass
     const int lane = threadIdx.x % L;
     const int grp = threadIdx.x / L;
@@ -125,9 +121,9 @@ __global__ void __launch_bounds__(CH) spmv_kernel(int rows, const int *__restric
     if (DOT) {
         __syncthreads();
         double c = kmc_chunk_reduce_256(prod[threadIdx.x], red);
-        if (threadIdx.x == 0) publish_partial(cm, 0, c);
-        if (last_cta(&st->cnt[0], &flag, cm.size > 1)) {
-            exchange_partials(cm, dot_seq);
+        if (threadIdx.x == 0) publish_partial(cm, 0, blockIdx.x, c);
+        if (last_cta(&st->cnt[0], &flag, false)) {
+            exchange_partials(cm, 0, 1, gridDim.x, dot_seq);
             double tot = kmc_final_reduce(cm.partials, cm.nchunks_global, red);
             if (threadIdx.x == 0) {
                 st->pAp = tot;
@@ -197,7 +193,7 @@ __global__ void __launch_bounds__(CH) spmv_staged_kernel(int rows, const int *__
     if (DOT) {
         __syncthreads();
         double c = kmc_chunk_reduce_256(prod[threadIdx.x], red);
-        if (threadIdx.x == 0) publish_partial(cm, 0, c);
+        if (threadIdx.x == 0) publish_partial(cm, 0, blockIdx.x, c);
         if (last_cta(&st->cnt[0], &flag, false)) {
             double tot = kmc_final_reduce(cm.partials, cm.nchunks_global, red);
             if (threadIdx.x == 0) {
@@ -208,31 +204,37 @@ __global__ void __launch_bounds__(CH) spmv_staged_kernel(int rows, const int *__
     }
 }
 
+// The three vector kernels below are persistent-style: a CTA walks chunks c = blockIdx.x, blockIdx.x + gridDim.x, ...
+// (one 256-row dot chunk per trip), so there is one "last CTA" election per CTA instead of one per chunk.
+
 // r = b - A x0 ; z = M^-1 r ; bb = b.b ; rz = r.z     (dist_conjugate_gradient.cpp:187-213)
-__global__ void __launch_bounds__(CH) cg_init_kernel(int rows, double *__restrict__ r, const double *__restrict__ Ap,
-                                                    const double *__restrict__ dinv, double *__restrict__ z, CommDev cm,
-                                                    unsigned long long dot_seq, CgState *__restrict__ st) {
+__global__ void __launch_bounds__(CH) cg_init_kernel(int rows, int nchunks, double *__restrict__ r,
+                                                    const double *__restrict__ Ap, const double *__restrict__ dinv,
+                                                    double *__restrict__ z, CommDev cm, unsigned long long dot_seq,
+                                                    CgState *__restrict__ st) {
     __shared__ double red[8];
     __shared__ int flag;
-    int i = blockIdx.x * CH + threadIdx.x;
-    double vbb = 0.0, vrz = 0.0;
-    if (i < rows) {
-        double b = r[i];
-        double ri = b - Ap[i];
-        double zi = ri * dinv[i];
-        r[i] = ri;
-        z[i] = zi;
-        vbb = b * b;
-        vrz = ri * zi;
+    for (int c = blockIdx.x; c < nchunks; c += gridDim.x) {
+        int i = c * CH + threadIdx.x;
+        double vbb = 0.0, vrz = 0.0;
+        if (i < rows) {
+            double b = r[i];
+            double ri = b - Ap[i];
+            double zi = ri * dinv[i];
+            r[i] = ri;
+            z[i] = zi;
+            vbb = b * b;
+            vrz = ri * zi;
+        }
+        double cbb = kmc_chunk_reduce_256(vbb, red);
+        double crz = kmc_chunk_reduce_256(vrz, red);
+        if (threadIdx.x == 0) {
+            publish_partial(cm, 2, c, cbb);
+            publish_partial(cm, 3, c, crz);
+        }
     }
-    double cbb = kmc_chunk_reduce_256(vbb, red);
-    double crz = kmc_chunk_reduce_256(vrz, red);
-    if (threadIdx.x == 0) {
-        publish_partial(cm, 2, cbb);
-        publish_partial(cm, 3, crz);
-    }
-    if (last_cta(&st->cnt[1], &flag, cm.size > 1)) {
-        exchange_partials(cm, dot_seq);
+    if (last_cta(&st->cnt[1], &flag, false)) {
+        exchange_partials(cm, 2, 2, nchunks, dot_seq);
         double bb = kmc_final_reduce(cm.partials + (size_t)2 * cm.nchunks_global, cm.nchunks_global, red);
         double rz = kmc_final_reduce(cm.partials + (size_t)3 * cm.nchunks_global, cm.nchunks_global, red);
         if (threadIdx.x == 0) {
@@ -249,40 +251,51 @@ __global__ void __launch_bounds__(CH) cg_init_kernel(int rows, double *__restric
 
 // MODE 1: p = z (k == 1)  or  p = z + (rz/rz_old) p      (dist_conjugate_gradient.cpp:218-227)
 // MODE 0: p = src (the copy of x0 at :178)
-// The new entries are written to this rank's p vector and, for rows a peer's block references, into the peer's.
+// The new entries are written to this rank's p vector and, for rows a peer's block references, straight into the
+// peer's p vector (halo push).  The last CTA raises the halo flag at the peers and waits for theirs, so when this kernel
+// has finished every halo entry this rank needs has arrived and the SpMV that follows needs no synchronisation.
 template <int MODE>
-__global__ void __launch_bounds__(256) cg_pupdate_kernel(int rows, const double *__restrict__ src,
-                                                        const double *__restrict__ p_old, double *__restrict__ p_new,
-                                                        CommDev cm, int buf, unsigned long long halo_seq,
-                                                        CgState *__restrict__ st) {
+__global__ void __launch_bounds__(CH) cg_pupdate_kernel(int rows, int nchunks, const double *__restrict__ src,
+                                                       const double *__restrict__ p_old, double *__restrict__ p_new,
+                                                       CommDev cm, int buf, unsigned long long halo_seq,
+                                                       CgState *__restrict__ st) {
     if (MODE == 1 && st->done) return;
     __shared__ int flag;
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < rows) {
-        const int g = cm.row_start + i;
-        double v;
-        if (MODE == 0 || st->k == 1) {
-            v = src[i];
-        } else {
-            double b = st->rz / st->rz_old;
-            double t = b * p_old[g];
-            v = src[i] + t;
-        }
-        p_new[g] = v;
-        if (cm.size > 1) {
-            unsigned m = cm.send_mask[i];
-            while (m) {
-                int q = __ffs(m) - 1;
-                m &= m - 1;
-                cm.peer_p_full[q][buf][g] = v;
+    const bool first = (MODE == 0) || (st->k == 1);
+    const double beta = first ? 0.0 : st->rz / st->rz_old;
+    int remote = 0;
+    for (int c = blockIdx.x; c < nchunks; c += gridDim.x) {
+        int i = c * CH + threadIdx.x;
+        if (i < rows) {
+            const int g = cm.row_start + i;
+            double v;
+            if (first) {
+                v = src[i];
+            } else {
+                double t = beta * p_old[g];
+                v = src[i] + t;
+            }
+            p_new[g] = v;
+            if (cm.size > 1) {
+                unsigned m = cm.send_mask[i];
+                remote |= (m != 0);
+                while (m) {
+                    int q = __ffs(m) - 1;
+                    m &= m - 1;
+                    cm.peer_p_full[q][buf][g] = v;
+                }
             }
         }
     }
     if (cm.size > 1) {
-        if (last_cta(&st->cnt[4], &flag, true)) {
+        remote = __syncthreads_or(remote);
+        if (last_cta(&st->cnt[4], &flag, remote != 0)) {
             if (threadIdx.x == 0) {
+                __threadfence_system();
                 for (int q = 0; q < cm.size; ++q)
                     if (q != cm.rank) kmc_store_release_sys(cm.peer_flag_halo[q] + cm.rank, halo_seq);
+                kmc_wait_flags(cm.flag_halo, cm.recv_mask, cm.rank, halo_seq);
+                __threadfence_system();
                 st->cnt[4] = 0;
             }
         }
@@ -290,7 +303,7 @@ __global__ void __launch_bounds__(256) cg_pupdate_kernel(int rows, const double 
 }
 
 // a = rz / p.Ap ; x += a p ; r -= a Ap ; z = M^-1 r ; rz' = r.z ; k++   (dist_conjugate_gradient.cpp:243-266)
-__global__ void __launch_bounds__(CH) cg_update_kernel(int rows, const double *__restrict__ p_full,
+__global__ void __launch_bounds__(CH) cg_update_kernel(int rows, int nchunks, const double *__restrict__ p_full,
                                                       const double *__restrict__ Ap, const double *__restrict__ dinv,
                                                       double *__restrict__ x, double *__restrict__ r,
                                                       double *__restrict__ z, CommDev cm, unsigned long long dot_seq,
@@ -300,22 +313,24 @@ __global__ void __launch_bounds__(CH) cg_update_kernel(int rows, const double *_
     __shared__ int flag;
     const double a = st->rz / st->pAp;
     const double na = -a;
-    int i = blockIdx.x * CH + threadIdx.x;
-    double v = 0.0;
-    if (i < rows) {
-        double pi = p_full[cm.row_start + i];
-        double xi = fma(a, pi, x[i]);
-        double ri = fma(na, Ap[i], r[i]);
-        double zi = ri * dinv[i];
-        x[i] = xi;
-        r[i] = ri;
-        z[i] = zi;
-        v = ri * zi;
+    for (int c = blockIdx.x; c < nchunks; c += gridDim.x) {
+        int i = c * CH + threadIdx.x;
+        double v = 0.0;
+        if (i < rows) {
+            double pi = p_full[cm.row_start + i];
+            double xi = fma(a, pi, x[i]);
+            double ri = fma(na, Ap[i], r[i]);
+            double zi = ri * dinv[i];
+            x[i] = xi;
+            r[i] = ri;
+            z[i] = zi;
+            v = ri * zi;
+        }
+        double cv = kmc_chunk_reduce_256(v, red);
+        if (threadIdx.x == 0) publish_partial(cm, 1, c, cv);
     }
-    double c = kmc_chunk_reduce_256(v, red);
-    if (threadIdx.x == 0) publish_partial(cm, 1, c);
-    if (last_cta(&st->cnt[2], &flag, cm.size > 1)) {
-        exchange_partials(cm, dot_seq);
+    if (last_cta(&st->cnt[2], &flag, false)) {
+        exchange_partials(cm, 1, 1, nchunks, dot_seq);
         double rz = kmc_final_reduce(cm.partials + (size_t)cm.nchunks_global, cm.nchunks_global, red);
         if (threadIdx.x == 0) {
             st->rz_old = st->rz;
@@ -406,10 +421,11 @@ static int push_vector(kmcb200_ctx *ctx, kmcb200_kmat *K, const double *x_local,
     kmcb200_comm *C = K->comm;
     const unsigned long long hs = ++C->halo_seq;
     const int buf = (int)(hs & 1);
-    const unsigned eb = (unsigned)((K->rows + 255) / 256);
+    const int nch = (K->rows + CH - 1) / CH;
+    const unsigned eb = (unsigned)(nch < ctx->sm_count * 8 ? (nch > 0 ? nch : 1) : ctx->sm_count * 8);
     kmc_count_launch();
-    cg_pupdate_kernel<0><<<eb, 256, 0, ctx->stream>>>(K->rows, x_local, nullptr, C->dev.p_full[buf], C->dev, buf, hs,
-                                                     ctx->cg_state);
+    cg_pupdate_kernel<0><<<eb, CH, 0, ctx->stream>>>(K->rows, nch, x_local, nullptr, C->dev.p_full[buf], C->dev, buf, hs,
+                                                    ctx->cg_state);
     KMC_CUDA(cudaGetLastError());
     *buf_out = buf;
     *halo_seq_out = hs;
@@ -474,7 +490,8 @@ extern "C" int kmcb200_pcg_jacobi(kmcb200_ctx *ctx, kmcb200_kmat *K, double *r_l
         KMC_TRY(spmv_launch(ctx, K, C->dev.p_full[buf], K->Ap, false, hs, 0));
     }
     kmc_count_launch();
-    cg_init_kernel<<<nchunks, CH, 0, ctx->stream>>>(rows, r_local, K->Ap, diag_inv_local, K->z, C->dev, ++C->dot_seq, st);
+    const unsigned eb = (unsigned)((int)nchunks < ctx->sm_count * 8 ? (nchunks > 0 ? nchunks : 1) : ctx->sm_count * 8);
+    cg_init_kernel<<<eb, CH, 0, ctx->stream>>>(rows, (int)nchunks, r_local, K->Ap, diag_inv_local, K->z, C->dev, ++C->dot_seq, st);
     KMC_CUDA(cudaGetLastError());
     int *h_flags = (int *)((char *)ctx->h_mail + 512);
     auto read_flags = [&]() -> int {
@@ -484,22 +501,45 @@ extern "C" int kmcb200_pcg_jacobi(kmcb200_ctx *ctx, kmcb200_kmat *K, double *r_l
     };
     KMC_TRY(read_flags());
     int batch = 4;
-    const unsigned eb = (unsigned)((rows + 255) / 256);
+    // KMCB200_PCG_PROFILE=1: CUDA events around every kernel of the iteration (diagnostics only; serialises nothing
+    // by itself, the events sit on the same stream)
+    static const bool profile = getenv("KMCB200_PCG_PROFILE") != nullptr;
+    cudaEvent_t pe[4] = {nullptr, nullptr, nullptr, nullptr};
+    double pt[3] = {0, 0, 0};
+    long pn = 0;
+    if (profile)
+        for (auto &e : pe) cudaEventCreate(&e);
     while (!h_flags[2]) {  // done
         for (int b = 0; b < batch; ++b) {
             const unsigned long long hs2 = ++C->halo_seq;
             const int nb = (int)(hs2 & 1);
+            const bool rec = profile && b == batch - 1;
+            if (rec) cudaEventRecord(pe[0], ctx->stream);
             kmc_count_launch();
-            cg_pupdate_kernel<1><<<eb, 256, 0, ctx->stream>>>(rows, K->z, C->dev.p_full[nb ^ 1], C->dev.p_full[nb], C->dev,
-                                                             nb, hs2, st);
+            cg_pupdate_kernel<1><<<eb, CH, 0, ctx->stream>>>(rows, (int)nchunks, K->z, C->dev.p_full[nb ^ 1], C->dev.p_full[nb],
+                                                            C->dev, nb, hs2, st);
+            if (rec) cudaEventRecord(pe[1], ctx->stream);
             KMC_TRY(spmv_launch(ctx, K, C->dev.p_full[nb], K->Ap, true, hs2, ++C->dot_seq));
+            if (rec) cudaEventRecord(pe[2], ctx->stream);
             kmc_count_launch();
-            cg_update_kernel<<<nchunks, CH, 0, ctx->stream>>>(rows, C->dev.p_full[nb], K->Ap, diag_inv_local, x_local,
-                                                             r_local, K->z, C->dev, ++C->dot_seq, st);
+            cg_update_kernel<<<eb, CH, 0, ctx->stream>>>(rows, (int)nchunks, C->dev.p_full[nb], K->Ap, diag_inv_local, x_local,
+                                                        r_local, K->z, C->dev, ++C->dot_seq, st);
+            if (rec) cudaEventRecord(pe[3], ctx->stream);
         }
         KMC_CUDA(cudaGetLastError());
         KMC_TRY(read_flags());
+        if (profile) {
+            float ms;
+            for (int q = 0; q < 3; ++q) { cudaEventElapsedTime(&ms, pe[q], pe[q + 1]); pt[q] += ms; }
+            pn++;
+        }
         if (batch < 32) batch *= 2;
+    }
+    if (profile) {
+        if (pn > 0)
+            fprintf(stderr, "[pcg profile] rank %d rows %d: pupdate %.1f us, spmv+dot %.1f us, update+dot %.1f us (avg of %ld samples)\n",
+                    C->rank, rows, 1e3 * pt[0] / pn, 1e3 * pt[1] / pn, 1e3 * pt[2] / pn, pn);
+        for (auto &e : pe) cudaEventDestroy(e);
     }
     if (iterations_host) *iterations_host = h_flags[3];
     return 0;

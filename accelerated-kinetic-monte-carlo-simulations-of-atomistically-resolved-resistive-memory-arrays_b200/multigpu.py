@@ -45,6 +45,28 @@ def recv_mask_numpy(my_need: np.ndarray, rank: int, counts, displs) -> int:
     return mask
 
 
+def balanced_partition(row_weight: np.ndarray, nranks: int, chunk: int = 256):
+    """Contiguous row blocks with boundaries on multiples of `chunk` rows and (nearly) equal total weight (non-zeros).
+    Any chunk-aligned partition gives bit-identical results; this one also balances the SpMV."""
+    n = len(row_weight)
+    nch = (n + chunk - 1) // chunk
+    pad = np.zeros(nch * chunk, dtype=np.int64)
+    pad[:n] = row_weight
+    cw = np.concatenate([[0], np.cumsum(pad.reshape(nch, chunk).sum(1))])
+    total = cw[-1]
+    bounds = [0]
+    for r in range(1, nranks):
+        target = total * r / nranks
+        b = int(np.searchsorted(cw, target))
+        if b > 0 and abs(cw[b - 1] - target) <= abs(cw[min(b, nch)] - target):
+            b -= 1
+        bounds.append(min(max(b, bounds[-1]), nch))
+    bounds.append(nch)
+    displs = np.minimum(np.array(bounds[:-1], dtype=np.int64) * chunk, n)
+    ends = np.minimum(np.array(bounds[1:], dtype=np.int64) * chunk, n)
+    return (ends - displs).astype(np.int32), displs.astype(np.int32)
+
+
 def allgather_slices(dist, local, counts, displs, out):
     """out[displs[q] : displs[q]+counts[q]] = rank q's `local` (uneven slices; equal-size padded all_gather)."""
     import torch
@@ -125,7 +147,11 @@ class DistributedDeviceKMC(DeviceKMC):
         self.pot_charge = c.empty_d(self.N, 0.0)
         self.neigh = c.compute_neighbor_list(self.x, self.y, self.z)
         n = s.N - s.N_left - s.N_right
-        self.counts_K, self.displs_K = partition(n, world, aligned=True)
+        if world > 1:   # nnz-balanced, chunk-aligned row blocks (every rank computes the same boundaries)
+            w = c.sparsity_K_row_counts(self.x, self.y, self.z, s.lattice, s.pbc, s.nn_dist, s.N_left, s.N_right)
+            self.counts_K, self.displs_K = balanced_partition(w.cpu().numpy(), world)
+        else:
+            self.counts_K, self.displs_K = partition(n, world, aligned=True)
         self.counts_N, self.displs_N = partition(s.N, world)
         self.comm = Comm(c, rank, world, n, self.counts_K, self.displs_K, dist)
         self.K = c.initialize_sparsity_K(self.x, self.y, self.z, s.lattice, s.pbc, s.nn_dist, s.N_left, s.N_right,

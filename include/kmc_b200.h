@@ -166,6 +166,10 @@ int kmcb200_background_potential(kmcb200_ctx *ctx, kmcb200_kmat *kmat, int N, in
  *      kmcb200_kmat_need_map -> all-gather the n_global-byte maps out of band -> kmcb200_comm_set_send_masks
  * afterwards kmcb200_pcg_jacobi / kmcb200_spmv / kmcb200_background_potential work on the sharded matrix and return
  * bit-identical results on every rank and for every rank count. */
+/* interior non-zeros per interior row, for all n rows (device int32[n]): input of an nnz-balanced partition */
+int kmcb200_sparsity_K_row_counts(kmcb200_ctx *ctx, int N, const double *x, const double *y, const double *z,
+                                  const double *lattice_host, int pbc, double nn_dist, int N_left, int N_right,
+                                  int *row_nnz_dev);
 int kmcb200_comm_create(kmcb200_ctx *ctx, int rank, int size, int n_global_rows, const int *counts_host,
                         const int *displs_host, kmcb200_comm **comm_out);
 int kmcb200_comm_destroy(kmcb200_comm *comm);

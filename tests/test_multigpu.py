@@ -93,6 +93,20 @@ def test_partition_aligned_matches_reference_arithmetic_on_chunks(kmc):
         assert [int(v) for v in (c + 255) // 256] == [int(v) for v in cc] or c[-1] == 0
 
 
+def test_balanced_partition(kmc):
+    mg = importlib.import_module(PKG + ".multigpu")
+    rng = np.random.default_rng(0)
+    w = np.concatenate([np.full(5000, 19), np.full(9000, 30), rng.integers(5, 54, 7000)])
+    for P in (1, 2, 3, 8):
+        c, d = mg.balanced_partition(w, P)
+        assert c.sum() == len(w) and d[0] == 0 and (np.diff(d) == c[:-1]).all()
+        assert all(int(v) % 256 == 0 for v in d)
+        loads = [int(w[d[q]:d[q] + c[q]].sum()) for q in range(P)]
+        assert max(loads) <= w.sum() / P + 256 * 54          # within one chunk of the ideal share
+    c, d = mg.balanced_partition(np.ones(100, dtype=np.int64), 4)   # fewer chunks than ranks: trailing ranks are empty
+    assert c.sum() == 100 and (c >= 0).all()
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("which", ["5nm", "file"])
 def test_sharded_solve_bit_identical_to_single_gpu(which):
