@@ -101,6 +101,7 @@ SIGNATURES = {
     "kmcb200_assemble_K": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _pi, _i, _d, _d, _d]),
     "kmcb200_pcg_jacobi": (_i, [_vp, _vp, _vp, _vp, _vp, _d, _i, _pi]),
     "kmcb200_spmv": (_i, [_vp, _vp, _vp, _vp]),
+    "kmcb200_spmv_dot": (_i, [_vp, _vp, _vp, _vp, _pd]),
     "kmcb200_dot": (_i, [_vp, _vp, _vp, _ll, _pd]),
     "kmcb200_background_potential": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _pi, _i, _d, _d, _d, _vp, _pi]),
     "kmcb200_sparsity_K_row_counts": (_i, [_vp, _i, _vp, _vp, _vp, _pd, _i, _d, _i, _i, _vp]),
@@ -382,6 +383,11 @@ class Context:
 
     def spmv(self, K, x, y):
         _check(self.lib.kmcb200_spmv(self.h, K.h, _ptr(x), _ptr(y)))
+
+    def spmv_dot(self, K, x, y, want_scalar=True):
+        out = C.c_double(0)
+        _check(self.lib.kmcb200_spmv_dot(self.h, K.h, _ptr(x), _ptr(y), C.byref(out) if want_scalar else None))
+        return out.value if want_scalar else None
 
     def dot(self, u, v) -> float:
         out = C.c_double(0)

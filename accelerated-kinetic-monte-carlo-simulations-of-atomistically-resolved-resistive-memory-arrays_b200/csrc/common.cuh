@@ -124,7 +124,16 @@ __device__ __forceinline__ double kmc_chunk_reduce_256(double v, double *sm) {
 // summation spec final_reduce over n partials (blockDim.x == 256); result valid in thread 0
 __device__ __forceinline__ double kmc_final_reduce(const double *partials, long long n, double *sm) {
     double acc = 0.0;
-    for (long long k = threadIdx.x; k < n; k += 256) acc = acc + __ldcg(partials + k);
+    long long k = threadIdx.x;
+    // 8 loads in flight per trip; the additions keep the sequential order k, k+256, k+512, ...
+    for (; k + 7 * 256 < n; k += 8 * 256) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldcg(partials + k + u * 256);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc = acc + v[u];
+    }
+    for (; k < n; k += 256) acc = acc + __ldcg(partials + k);
     return kmc_chunk_reduce_256(acc, sm);
 }
 // summation spec block_scan_256 (Kogge-Stone in warps, sequential over the 8 warp totals).

@@ -46,10 +46,21 @@ __device__ __forceinline__ void exchange_partials(const CommDev &cm, int slot0, 
     if (cm.size > 1) {
         for (int sidx = 0; sidx < nslots; ++sidx) {
             const size_t base = (size_t)(slot0 + sidx) * cm.nchunks_global + cm.chunk_start;
-            for (int i = threadIdx.x; i < local_chunks; i += blockDim.x) {
-                const double v = __ldcg(cm.partials + base + i);
-                for (int q = 0; q < cm.size; ++q)
-                    if (q != cm.rank) cm.peer_partials[q][base + i] = v;
+            for (int i0 = threadIdx.x; i0 < local_chunks; i0 += 8 * blockDim.x) {
+                double v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int i = i0 + u * blockDim.x;
+                    v[u] = (i < local_chunks) ? __ldcg(cm.partials + base + i) : 0.0;
+                }
+                for (int q = 0; q < cm.size; ++q) {
+                    if (q == cm.rank) continue;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int i = i0 + u * blockDim.x;
+                        if (i < local_chunks) cm.peer_partials[q][base + i] = v[u];
+                    }
+                }
             }
         }
         __threadfence_system();
@@ -63,19 +74,67 @@ __device__ __forceinline__ void exchange_partials(const CommDev &cm, int slot0, 
         __syncthreads();
     }
 }
+// ---- completion of a dot product: exchange the partials with the peers, reduce ALL partials in the fixed order, update
+// the PCG state.  Runs either in the last CTA of the producing kernel (small problems: saves a launch) or in the 1-CTA
+// dot_finalize_kernel (large problems: the producing kernel's CTAs then need no fence / atomic at all).
+__device__ __forceinline__ void finish_pap(const CommDev &cm, int local_chunks, unsigned long long seq, CgState *st,
+                                           double *red) {
+    exchange_partials(cm, 0, 1, local_chunks, seq);
+    double tot = kmc_final_reduce(cm.partials, cm.nchunks_global, red);
+    if (threadIdx.x == 0) st->pAp = tot;
+}
+__device__ __forceinline__ void finish_rz(const CommDev &cm, int local_chunks, unsigned long long seq, CgState *st,
+                                          double *red) {
+    exchange_partials(cm, 1, 1, local_chunks, seq);
+    double rz = kmc_final_reduce(cm.partials + (size_t)cm.nchunks_global, cm.nchunks_global, red);
+    if (threadIdx.x == 0) {
+        st->rz_old = st->rz;
+        st->rz = rz;
+        int k = st->k + 1;
+        st->k = k;
+        st->iters = k - 1;
+        st->done = !(rz / st->bb > st->tol2 && k <= st->max_it);
+    }
+}
+__device__ __forceinline__ void finish_init(const CommDev &cm, int local_chunks, unsigned long long seq, CgState *st,
+                                            double *red) {
+    exchange_partials(cm, 2, 2, local_chunks, seq);
+    double bb = kmc_final_reduce(cm.partials + (size_t)2 * cm.nchunks_global, cm.nchunks_global, red);
+    double rz = kmc_final_reduce(cm.partials + (size_t)3 * cm.nchunks_global, cm.nchunks_global, red);
+    if (threadIdx.x == 0) {
+        st->bb = bb;
+        st->rz = rz;
+        st->rz_old = 0.0;
+        st->k = 1;
+        st->iters = 0;
+        st->done = !(rz / bb > st->tol2 && 1 <= st->max_it);
+    }
+}
+// kind: 0 = p.Ap, 1 = r.z (+ iteration bookkeeping), 2 = setup (b.b and r.z)
+__global__ void __launch_bounds__(CH) dot_finalize_kernel(CommDev cm, int kind, int local_chunks, unsigned long long seq,
+                                                         CgState *__restrict__ st) {
+    __shared__ double red[8];
+    if (kind != 2 && st->done) return;
+    if (kind == 0) finish_pap(cm, local_chunks, seq, st, red);
+    else if (kind == 1) finish_rz(cm, local_chunks, seq, st, red);
+    else finish_init(cm, local_chunks, seq, st, red);
+}
+
 // y = A x (x indexed by GLOBAL column), optional fused partial of  x[row].y[row]  (p.Ap)
 // Row reduction spec: L lanes per row, lane l accumulates entries l, l+L, ... with fma in increasing k,
 // then a butterfly over the L lanes.
-template <int L, bool DOT>
+// FUSE: the last CTA completes the dot product (small problems).  Keeping that cold path out of the FUSE=false
+// instantiation matters: its register pressure would otherwise cap the occupancy of the hot loop (48-64 vs 32 regs).
+template <int L, bool DOT, int DEPTH, bool FUSE>
 __global__ void __launch_bounds__(CH) spmv_kernel(int rows, const int *__restrict__ row_ptr,
                                                  const int *__restrict__ col, const double *__restrict__ val,
                                                  const double *__restrict__ xg, double *__restrict__ y, CommDev cm,
-                                                 unsigned long long halo_seq, unsigned long long dot_seq,
-                                                 CgState *__restrict__ st) {
+                                                 unsigned long long dot_seq, CgState *__restrict__ st) {
     if (DOT && st->done) return;
-    __shared__ double prod[CH];
+    __shared__ double prod[DOT ? CH : 1];
     __shared__ double red[8];
     __shared__ int flag;
+    (void)flag;
     constexpr int GROUPS = CH / L;  // rows per pass
     const int lane = threadIdx.x % L;
     const int grp = threadIdx.x / L;
@@ -89,7 +148,6 @@ __global__ void __launch_bounds__(CH) spmv_kernel(int rows, const int *__restric
             const int s = row_ptr[r], e = row_ptr[r + 1];
             // all of this lane's entries (k = s+lane, s+lane+L, ...) are loaded before the FMA chain starts, so a lane
             // keeps up to DEPTH (val, col, x) triples in flight instead of one; the FMA order is unchanged.
-            constexpr int DEPTH = 7;  // covers rows of up to 56 entries in one trip
             for (int k0 = s + lane; k0 < e; k0 += L * DEPTH) {
                 double v[DEPTH], xv[DEPTH];
                 int c[DEPTH];
@@ -122,12 +180,10 @@ __global__ void __launch_bounds__(CH) spmv_kernel(int rows, const int *__restric
         __syncthreads();
         double c = kmc_chunk_reduce_256(prod[threadIdx.x], red);
         if (threadIdx.x == 0) publish_partial(cm, 0, blockIdx.x, c);
-        if (last_cta(&st->cnt[0], &flag, false)) {
-            exchange_partials(cm, 0, 1, gridDim.x, dot_seq);
-            double tot = kmc_final_reduce(cm.partials, cm.nchunks_global, red);
-            if (threadIdx.x == 0) {
-                st->pAp = tot;
-                st->cnt[0] = 0;
+        if (FUSE) {
+            if (last_cta(&st->cnt[0], &flag, false)) {
+                finish_pap(cm, gridDim.x, dot_seq, st, red);
+                if (threadIdx.x == 0) st->cnt[0] = 0;
             }
         }
     }
@@ -208,21 +264,22 @@ __global__ void __launch_bounds__(CH) spmv_staged_kernel(int rows, const int *__
 // (one 256-row dot chunk per trip), so there is one "last CTA" election per CTA instead of one per chunk.
 
 // r = b - A x0 ; z = M^-1 r ; bb = b.b ; rz = r.z     (dist_conjugate_gradient.cpp:187-213)
+template <bool FUSE>
 __global__ void __launch_bounds__(CH) cg_init_kernel(int rows, int nchunks, double *__restrict__ r,
                                                     const double *__restrict__ Ap, const double *__restrict__ dinv,
-                                                    double *__restrict__ z, CommDev cm, unsigned long long dot_seq,
-                                                    CgState *__restrict__ st) {
+                                                    double *__restrict__ z, CommDev cm,
+                                                    unsigned long long dot_seq, CgState *__restrict__ st) {
     __shared__ double red[8];
     __shared__ int flag;
     for (int c = blockIdx.x; c < nchunks; c += gridDim.x) {
         int i = c * CH + threadIdx.x;
         double vbb = 0.0, vrz = 0.0;
         if (i < rows) {
-            double b = r[i];
-            double ri = b - Ap[i];
-            double zi = ri * dinv[i];
-            r[i] = ri;
-            z[i] = zi;
+            double b = __ldcs(r + i);
+            double ri = b - __ldcs(Ap + i);
+            double zi = ri * __ldcs(dinv + i);
+            __stcs(r + i, ri);
+            __stcs(z + i, zi);
             vbb = b * b;
             vrz = ri * zi;
         }
@@ -233,18 +290,10 @@ __global__ void __launch_bounds__(CH) cg_init_kernel(int rows, int nchunks, doub
             publish_partial(cm, 3, c, crz);
         }
     }
-    if (last_cta(&st->cnt[1], &flag, false)) {
-        exchange_partials(cm, 2, 2, nchunks, dot_seq);
-        double bb = kmc_final_reduce(cm.partials + (size_t)2 * cm.nchunks_global, cm.nchunks_global, red);
-        double rz = kmc_final_reduce(cm.partials + (size_t)3 * cm.nchunks_global, cm.nchunks_global, red);
-        if (threadIdx.x == 0) {
-            st->bb = bb;
-            st->rz = rz;
-            st->rz_old = 0.0;
-            st->k = 1;
-            st->iters = 0;
-            st->done = !(rz / bb > st->tol2 && 1 <= st->max_it);
-            st->cnt[1] = 0;
+    if (FUSE) {
+        if (last_cta(&st->cnt[1], &flag, false)) {
+            finish_init(cm, nchunks, dot_seq, st, red);
+            if (threadIdx.x == 0) st->cnt[1] = 0;
         }
     }
 }
@@ -269,11 +318,12 @@ __global__ void __launch_bounds__(CH) cg_pupdate_kernel(int rows, int nchunks, c
         if (i < rows) {
             const int g = cm.row_start + i;
             double v;
+            // streaming (evict-first) reads: only the new p must stay L2 resident for the SpMV gathers
             if (first) {
-                v = src[i];
+                v = __ldcs(src + i);
             } else {
-                double t = beta * p_old[g];
-                v = src[i] + t;
+                double t = beta * __ldcs(p_old + g);
+                v = __ldcs(src + i) + t;
             }
             p_new[g] = v;
             if (cm.size > 1) {
@@ -303,11 +353,12 @@ __global__ void __launch_bounds__(CH) cg_pupdate_kernel(int rows, int nchunks, c
 }
 
 // a = rz / p.Ap ; x += a p ; r -= a Ap ; z = M^-1 r ; rz' = r.z ; k++   (dist_conjugate_gradient.cpp:243-266)
+template <bool FUSE>
 __global__ void __launch_bounds__(CH) cg_update_kernel(int rows, int nchunks, const double *__restrict__ p_full,
                                                       const double *__restrict__ Ap, const double *__restrict__ dinv,
                                                       double *__restrict__ x, double *__restrict__ r,
-                                                      double *__restrict__ z, CommDev cm, unsigned long long dot_seq,
-                                                      CgState *__restrict__ st) {
+                                                      double *__restrict__ z, CommDev cm,
+                                                      unsigned long long dot_seq, CgState *__restrict__ st) {
     if (st->done) return;
     __shared__ double red[8];
     __shared__ int flag;
@@ -318,28 +369,21 @@ __global__ void __launch_bounds__(CH) cg_update_kernel(int rows, int nchunks, co
         double v = 0.0;
         if (i < rows) {
             double pi = p_full[cm.row_start + i];
-            double xi = fma(a, pi, x[i]);
-            double ri = fma(na, Ap[i], r[i]);
-            double zi = ri * dinv[i];
-            x[i] = xi;
-            r[i] = ri;
-            z[i] = zi;
+            double xi = fma(a, pi, __ldcs(x + i));
+            double ri = fma(na, __ldcs(Ap + i), __ldcs(r + i));
+            double zi = ri * __ldcs(dinv + i);
+            __stcs(x + i, xi);
+            __stcs(r + i, ri);
+            __stcs(z + i, zi);
             v = ri * zi;
         }
         double cv = kmc_chunk_reduce_256(v, red);
         if (threadIdx.x == 0) publish_partial(cm, 1, c, cv);
     }
-    if (last_cta(&st->cnt[2], &flag, false)) {
-        exchange_partials(cm, 1, 1, nchunks, dot_seq);
-        double rz = kmc_final_reduce(cm.partials + (size_t)cm.nchunks_global, cm.nchunks_global, red);
-        if (threadIdx.x == 0) {
-            st->rz_old = st->rz;
-            st->rz = rz;
-            int k = st->k + 1;
-            st->k = k;
-            st->iters = k - 1;
-            st->done = !(rz / st->bb > st->tol2 && k <= st->max_it);
-            st->cnt[2] = 0;
+    if (FUSE) {
+        if (last_cta(&st->cnt[2], &flag, false)) {
+            finish_rz(cm, nchunks, dot_seq, st, red);
+            if (threadIdx.x == 0) st->cnt[2] = 0;
         }
     }
 }
@@ -382,8 +426,10 @@ int ensure_cg_workspace(kmcb200_ctx *ctx, long long nchunks) {
 
 // y = A xg for this rank's rows; xg is indexed by global row and must already hold the halo entries (or be awaited
 // through halo_seq).  with_dot: fused p.Ap into CgState::pAp.
-static int spmv_launch(kmcb200_ctx *ctx, kmcb200_kmat *K, const double *xg, double *y, bool with_dot,
-                       unsigned long long halo_seq, unsigned long long dot_seq) {
+// fuse_final: the SpMV's last CTA completes the dot product itself (small problems); otherwise the caller launches
+// dot_finalize_kernel afterwards.
+static int spmv_launch(kmcb200_ctx *ctx, kmcb200_kmat *K, const double *xg, double *y, bool with_dot, int fuse_final,
+                       unsigned long long dot_seq) {
     constexpr int L = KMCB200_SPMV_LANES;
     const CommDev &cm = K->comm->dev;
     unsigned blocks = (unsigned)((K->rows + CH - 1) / CH);
@@ -404,12 +450,19 @@ static int spmv_launch(kmcb200_ctx *ctx, kmcb200_kmat *K, const double *xg, doub
         else
             spmv_staged_kernel<L, false><<<blocks, CH, dyn, ctx->stream>>>(K->rows, K->row_ptr, K->lcol, K->val, K->u_ptr,
                                                                           K->u_col, xg, y, cm, ctx->cg_state);
-    } else if (with_dot) {
-        spmv_kernel<L, true><<<blocks, CH, 0, ctx->stream>>>(K->rows, K->row_ptr, K->col, K->val, xg, y, cm, halo_seq,
-                                                            dot_seq, ctx->cg_state);
     } else {
-        spmv_kernel<L, false><<<blocks, CH, 0, ctx->stream>>>(K->rows, K->row_ptr, K->col, K->val, xg, y, cm, halo_seq,
-                                                             dot_seq, ctx->cg_state);
+        static const int depth = getenv("KMCB200_SPMV_DEPTH") ? atoi(getenv("KMCB200_SPMV_DEPTH")) : 4;
+#define KMC_SPMV_GO(DOTV, D, F)                                                                                  \
+    spmv_kernel<L, DOTV, D, F><<<blocks, CH, 0, ctx->stream>>>(K->rows, K->row_ptr, K->col, K->val, xg, y, cm, dot_seq, \
+                                                              ctx->cg_state)
+        if (with_dot && fuse_final) {
+            if (depth <= 4) KMC_SPMV_GO(true, 4, true); else KMC_SPMV_GO(true, 7, true);
+        } else if (with_dot) {
+            if (depth <= 4) KMC_SPMV_GO(true, 4, false); else KMC_SPMV_GO(true, 7, false);
+        } else {
+            if (depth <= 4) KMC_SPMV_GO(false, 4, false); else KMC_SPMV_GO(false, 7, false);
+        }
+#undef KMC_SPMV_GO
     }
     KMC_CUDA(cudaGetLastError());
     return 0;
@@ -436,11 +489,39 @@ extern "C" int kmcb200_spmv(kmcb200_ctx *ctx, kmcb200_kmat *K, const double *x_l
     KMC_CHECK_ARG(ctx && K && x_local && y_local, "null pointer");
     KMC_CHECK_ARG(K->comm != nullptr, "kmat has no exchange plan");
     KMC_TRY(ensure_cg_workspace(ctx, 1));
-    if (K->comm->size == 1) return spmv_launch(ctx, K, x_local, y_local, false, 0, 0);
+    static const bool force_dot = getenv("KMCB200_SPMV_FORCE_DOT") != nullptr;  // diagnostics: time the dot variant
+    if (K->comm->size == 1) return spmv_launch(ctx, K, x_local, y_local, force_dot, 0, 0);
     int buf;
     unsigned long long hs;
     KMC_TRY(push_vector(ctx, K, x_local, &buf, &hs));
-    return spmv_launch(ctx, K, K->comm->dev.p_full[buf], y_local, false, hs, 0);
+    (void)hs;
+    return spmv_launch(ctx, K, K->comm->dev.p_full[buf], y_local, false, 1, 0);
+}
+
+// y = A x and x.(A x) in one pass: the fused kernel the PCG iteration uses (single rank; x_local is the full vector).
+// The scalar is left on the device (CgState::pAp) unless dot_host != NULL (then: host sync).
+extern "C" int kmcb200_spmv_dot(kmcb200_ctx *ctx, kmcb200_kmat *K, const double *x_local, double *y_local,
+                                double *dot_host) {
+    KMC_CHECK_ARG(ctx && K && x_local && y_local, "null pointer");
+    KMC_CHECK_ARG(K->comm != nullptr && K->comm->size == 1, "kmcb200_spmv_dot is a single-rank call");
+    const int nchunks = (K->rows + CH - 1) / CH;
+    KMC_TRY(ensure_cg_workspace(ctx, nchunks));
+    CgState *st = ctx->cg_state;
+    KMC_CUDA(cudaMemsetAsync(&st->done, 0, sizeof(int), ctx->stream));
+    const int fuse = nchunks <= 1024 ? 1 : 0;
+    const unsigned long long ds = ++K->comm->dot_seq;
+    KMC_TRY(spmv_launch(ctx, K, x_local, y_local, true, fuse, ds));
+    if (!fuse) {
+        kmc_count_launch();
+        dot_finalize_kernel<<<1, CH, 0, ctx->stream>>>(K->comm->dev, 0, nchunks, ds, st);
+        KMC_CUDA(cudaGetLastError());
+    }
+    if (dot_host) {
+        KMC_CUDA(cudaMemcpyAsync(ctx->h_mail, &st->pAp, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        KMC_CUDA(cudaStreamSynchronize(ctx->stream));
+        *dot_host = *(double *)ctx->h_mail;
+    }
+    return 0;
 }
 
 extern "C" int kmcb200_dot(kmcb200_ctx *ctx, const double *u, const double *v, long long n, double *result_host) {
@@ -482,16 +563,25 @@ extern "C" int kmcb200_pcg_jacobi(kmcb200_ctx *ctx, kmcb200_kmat *K, double *r_l
     int buf = 0;
     unsigned long long hs = 0;
     if (C->size == 1) {
-        KMC_TRY(spmv_launch(ctx, K, x_local, K->Ap, false, 0, 0));
+        KMC_TRY(spmv_launch(ctx, K, x_local, K->Ap, false, 1, 0));
         hs = C->halo_seq;
         buf = (int)(hs & 1);
     } else {
         KMC_TRY(push_vector(ctx, K, x_local, &buf, &hs));
-        KMC_TRY(spmv_launch(ctx, K, C->dev.p_full[buf], K->Ap, false, hs, 0));
+        KMC_TRY(spmv_launch(ctx, K, C->dev.p_full[buf], K->Ap, false, 1, 0));
     }
     kmc_count_launch();
     const unsigned eb = (unsigned)((int)nchunks < ctx->sm_count * 8 ? (nchunks > 0 ? nchunks : 1) : ctx->sm_count * 8);
-    cg_init_kernel<<<eb, CH, 0, ctx->stream>>>(rows, (int)nchunks, r_local, K->Ap, diag_inv_local, K->z, C->dev, ++C->dot_seq, st);
+    // Large problems: the dot products are completed by a separate 1-CTA kernel, so the thousands of producing CTAs need
+    // no fence + atomic election (measured: 13-26 % of the SpMV at >= 62 M non-zeros).  Small problems keep the fused
+    // last-CTA completion and save the launches.
+    const int fuse = nchunks <= 1024 ? 1 : 0;
+    {
+        const unsigned long long ds = ++C->dot_seq;
+        if (fuse) cg_init_kernel<true><<<eb, CH, 0, ctx->stream>>>(rows, (int)nchunks, r_local, K->Ap, diag_inv_local, K->z, C->dev, ds, st);
+        else cg_init_kernel<false><<<eb, CH, 0, ctx->stream>>>(rows, (int)nchunks, r_local, K->Ap, diag_inv_local, K->z, C->dev, ds, st);
+        if (!fuse) { kmc_count_launch(); dot_finalize_kernel<<<1, CH, 0, ctx->stream>>>(C->dev, 2, (int)nchunks, ds, st); }
+    }
     KMC_CUDA(cudaGetLastError());
     int *h_flags = (int *)((char *)ctx->h_mail + 512);
     auto read_flags = [&]() -> int {
@@ -504,42 +594,70 @@ extern "C" int kmcb200_pcg_jacobi(kmcb200_ctx *ctx, kmcb200_kmat *K, double *r_l
     // KMCB200_PCG_PROFILE=1: CUDA events around every kernel of the iteration (diagnostics only; serialises nothing
     // by itself, the events sit on the same stream)
     static const bool profile = getenv("KMCB200_PCG_PROFILE") != nullptr;
-    cudaEvent_t pe[4] = {nullptr, nullptr, nullptr, nullptr};
-    double pt[3] = {0, 0, 0};
+    static cudaEvent_t pev[4 * 32];
+    static bool pev_init = false;
+    cudaEvent_t pall[2] = {nullptr, nullptr};
+    double pt[3] = {0, 0, 0}, pgap = 0;
     long pn = 0;
-    if (profile)
-        for (auto &e : pe) cudaEventCreate(&e);
+    if (profile) {
+        if (!pev_init) { for (auto &e : pev) cudaEventCreate(&e); pev_init = true; }
+        for (auto &e : pall) cudaEventCreate(&e);
+        cudaEventRecord(pall[0], ctx->stream);
+    }
+    int launched_iters = 0;
     while (!h_flags[2]) {  // done
         for (int b = 0; b < batch; ++b) {
             const unsigned long long hs2 = ++C->halo_seq;
             const int nb = (int)(hs2 & 1);
-            const bool rec = profile && b == batch - 1;
+            const bool rec = profile;
+            cudaEvent_t *pe = pev + 4 * b;
             if (rec) cudaEventRecord(pe[0], ctx->stream);
             kmc_count_launch();
             cg_pupdate_kernel<1><<<eb, CH, 0, ctx->stream>>>(rows, (int)nchunks, K->z, C->dev.p_full[nb ^ 1], C->dev.p_full[nb],
                                                             C->dev, nb, hs2, st);
             if (rec) cudaEventRecord(pe[1], ctx->stream);
-            KMC_TRY(spmv_launch(ctx, K, C->dev.p_full[nb], K->Ap, true, hs2, ++C->dot_seq));
+            {
+                const unsigned long long ds = ++C->dot_seq;
+                KMC_TRY(spmv_launch(ctx, K, C->dev.p_full[nb], K->Ap, true, fuse, ds));
+                if (!fuse) { kmc_count_launch(); dot_finalize_kernel<<<1, CH, 0, ctx->stream>>>(C->dev, 0, (int)nchunks, ds, st); }
+            }
             if (rec) cudaEventRecord(pe[2], ctx->stream);
             kmc_count_launch();
-            cg_update_kernel<<<eb, CH, 0, ctx->stream>>>(rows, (int)nchunks, C->dev.p_full[nb], K->Ap, diag_inv_local, x_local,
-                                                        r_local, K->z, C->dev, ++C->dot_seq, st);
+            {
+                const unsigned long long ds = ++C->dot_seq;
+                if (fuse)
+                    cg_update_kernel<true><<<eb, CH, 0, ctx->stream>>>(rows, (int)nchunks, C->dev.p_full[nb], K->Ap, diag_inv_local,
+                                                                      x_local, r_local, K->z, C->dev, ds, st);
+                else
+                    cg_update_kernel<false><<<eb, CH, 0, ctx->stream>>>(rows, (int)nchunks, C->dev.p_full[nb], K->Ap, diag_inv_local,
+                                                                       x_local, r_local, K->z, C->dev, ds, st);
+                if (!fuse) { kmc_count_launch(); dot_finalize_kernel<<<1, CH, 0, ctx->stream>>>(C->dev, 1, (int)nchunks, ds, st); }
+            }
             if (rec) cudaEventRecord(pe[3], ctx->stream);
+            launched_iters++;
         }
         KMC_CUDA(cudaGetLastError());
         KMC_TRY(read_flags());
         if (profile) {
             float ms;
-            for (int q = 0; q < 3; ++q) { cudaEventElapsedTime(&ms, pe[q], pe[q + 1]); pt[q] += ms; }
-            pn++;
+            for (int b = 0; b < batch; ++b) {
+                for (int q = 0; q < 3; ++q) { cudaEventElapsedTime(&ms, pev[4 * b + q], pev[4 * b + q + 1]); pt[q] += ms; if (q == 1 && getenv("KMCB200_PCG_PROFILE_VERBOSE")) fprintf(stderr, "%.0f ", 1e3 * ms); }
+                if (b + 1 < batch) { cudaEventElapsedTime(&ms, pev[4 * b + 3], pev[4 * (b + 1)]); pgap += ms; }
+                pn++;
+            }
         }
         if (batch < 32) batch *= 2;
     }
     if (profile) {
+        float tot = 0;
+        cudaEventRecord(pall[1], ctx->stream);
+        cudaEventSynchronize(pall[1]);
+        cudaEventElapsedTime(&tot, pall[0], pall[1]);
+        fprintf(stderr, "[pcg profile] loop total %.3f ms for %d launched iterations (%d converged)\n", tot, launched_iters, h_flags[3]);
         if (pn > 0)
-            fprintf(stderr, "[pcg profile] rank %d rows %d: pupdate %.1f us, spmv+dot %.1f us, update+dot %.1f us (avg of %ld samples)\n",
-                    C->rank, rows, 1e3 * pt[0] / pn, 1e3 * pt[1] / pn, 1e3 * pt[2] / pn, pn);
-        for (auto &e : pe) cudaEventDestroy(e);
+            fprintf(stderr, "[pcg profile] rank %d rows %d: pupdate %.1f us, spmv+dot %.1f us, update+dot %.1f us, gap %.1f us (avg of %ld launched iterations; sums %.2f %.2f %.2f ms)\n",
+                    C->rank, rows, 1e3 * pt[0] / pn, 1e3 * pt[1] / pn, 1e3 * pt[2] / pn, 1e3 * pgap / pn, pn, pt[0], pt[1], pt[2]);
+        for (auto &e : pall) cudaEventDestroy(e);
     }
     if (iterations_host) *iterations_host = h_flags[3];
     return 0;

@@ -144,6 +144,9 @@ int kmcb200_pcg_jacobi(kmcb200_ctx *ctx, kmcb200_kmat *kmat, double *r_local, do
                        int *iterations_host);
 /* y = A x (x: this rank's rows; halo handled internally).  dspmv::gpu_packing_cam equivalent. */
 int kmcb200_spmv(kmcb200_ctx *ctx, kmcb200_kmat *kmat, const double *x_local, double *y_local);
+/* y = A x and x.(A x) in one pass (the fused SpMV + p.Ap kernel of the PCG iteration); single rank.  dot_host may be
+ * NULL (no host sync; the scalar stays on the device). */
+int kmcb200_spmv_dot(kmcb200_ctx *ctx, kmcb200_kmat *kmat, const double *x_local, double *y_local, double *dot_host);
 /* deterministic dot product of the summation spec (hipblasDdot + MPI_Allreduce replacement) */
 int kmcb200_dot(kmcb200_ctx *ctx, const double *u, const double *v, long long n, double *result_host);
 

@@ -128,6 +128,9 @@ def test_dot_and_spmv_bit_exact(ctx, orc, dev5, orc5, s5):
     ctx.spmv(dev5.K, ctx.dev_d(xv), y)
     want = orc.spmv(K["row_ptr"], K["col"], K["val"], xv)
     assert (to_np(y) == want).all()
+    y2 = ctx.empty_d(dev5.K.rows)
+    d = ctx.spmv_dot(dev5.K, ctx.dev_d(xv), y2)          # fused SpMV + x.(Ax), the PCG's hot kernel
+    assert (to_np(y2) == want).all() and d == orc.dot(xv, want)
 
 
 # ---------------------------------------------------------------- a7: PCG, same iteration count, bit-identical iterates
