@@ -67,7 +67,7 @@ __device__ __forceinline__ void exchange_partials(const CommDev &cm, int slot0, 
         __syncthreads();
         if (threadIdx.x == 0) {
             for (int q = 0; q < cm.size; ++q)
-                if (q != cm.rank) kmc_store_release_sys(cm.peer_flag_dot[q] + cm.rank, seq);
+                if (q != cm.rank) kmc_store_relaxed_sys(cm.peer_flag_dot[q] + cm.rank, seq);
             kmc_wait_flags(cm.flag_dot, (1u << cm.size) - 1u, cm.rank, seq);
             __threadfence_system();
         }
@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(CH) cg_pupdate_kernel(int rows, int nchunks, c
             if (threadIdx.x == 0) {
                 __threadfence_system();
                 for (int q = 0; q < cm.size; ++q)
-                    if (q != cm.rank) kmc_store_release_sys(cm.peer_flag_halo[q] + cm.rank, halo_seq);
+                    if (q != cm.rank) kmc_store_relaxed_sys(cm.peer_flag_halo[q] + cm.rank, halo_seq);
                 kmc_wait_flags(cm.flag_halo, cm.recv_mask, cm.rank, halo_seq);
                 __threadfence_system();
                 st->cnt[4] = 0;
