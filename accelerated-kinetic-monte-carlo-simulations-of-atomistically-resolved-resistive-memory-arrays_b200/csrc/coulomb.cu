@@ -58,8 +58,8 @@ struct __align__(16) Source {
 __global__ void charged_scatter_kernel(const int *__restrict__ charge, const int *__restrict__ element,
                                        const double *__restrict__ x, const double *__restrict__ y,
                                        const double *__restrict__ z, int N, const int *__restrict__ offs,
-                                       const int *__restrict__ site_cell, int ny, int nz, Source *__restrict__ src,
-                                       int *__restrict__ src_cell) {
+                                       const int *__restrict__ site_cell, Source *__restrict__ src,
+                                       int *__restrict__ src_cell, int *__restrict__ src_cell_count) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     if (charge[i] != 0 && kmc_possibly_charged(element[i])) {
@@ -68,7 +68,8 @@ __global__ void charged_scatter_kernel(const int *__restrict__ charge, const int
         int o = offs[i];
         src[o] = s;
         const int sc = site_cell[i];
-        src_cell[o] = (sc / (ny * nz)) | (((sc / nz) % ny) << 10) | ((sc % nz) << 20);  // packed (a, b, d)
+        src_cell[o] = sc;
+        atomicAdd(src_cell_count + sc, 1);
     }
 }
 
@@ -105,40 +106,105 @@ __global__ void block_map_kernel(const int *__restrict__ blk_start, int ncell, i
 }
 
 // ---- per step: ascending-j list of the charged sources in the 27-cell neighbourhood of every cell ----------
-// One WARP per cell walks the (ascending j) compacted source list 32 sources at a time; ballot + popc give each
-// matching source its ordered position, so the per-cell lists stay in ascending j.  Source cells are stored as
-// packed (a, b, d) coordinates (10 bits each) to keep the inner loop division free.
-template <bool FILL>
-__global__ void __launch_bounds__(128) cell_sources_kernel(int nx, int ny, int nz, const int *__restrict__ src_cell,
-                                                          const int *__restrict__ nsrc_ptr,
-                                                          const int *__restrict__ cell_tstart,
-                                                          int *__restrict__ cnt_or_start, int *__restrict__ lists) {
-    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    const int ncell = nx * ny * nz;
+// Sources are binned by cell (count / scan / atomic fill: unordered inside a cell); then one CTA per target cell
+// gathers the source ids of its <= 27 neighbour cells into shared memory, sorts them (bitonic) and writes the list,
+// so every target still sums its sources in ascending j.  O(Q) binning + O(m log^2 m) per cell instead of scanning all
+// Q sources for every cell.
+__global__ void src_bin_fill_kernel(int Q, const int *__restrict__ src_cell, const int *__restrict__ cstart,
+                                    int *__restrict__ fill, int *__restrict__ src_by_cell) {
+    int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= Q) return;
+    int c = src_cell[q];
+    src_by_cell[cstart[c] + atomicAdd(fill + c, 1)] = q;
+}
+
+// neighbourhood size of every cell that holds targets of the requested row range
+__global__ void nbr_count_kernel(int nx, int ny, int nz, const int *__restrict__ cstart,
+                                 const int *__restrict__ cell_min, const int *__restrict__ cell_max, int row_lo,
+                                 int row_hi, int *__restrict__ cnt, int *__restrict__ max_cnt) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    int ncell = nx * ny * nz;
     if (c > ncell) return;
-    if (c == ncell) {
-        if (!FILL && lane == 0) cnt_or_start[c] = 0;
-        return;
-    }
-    const bool active = cell_tstart[c + 1] > cell_tstart[c];  // cells without targets need no list
-    const int a = c / (ny * nz), b = (c / nz) % ny, d = c % nz;
-    const int Q = active ? *nsrc_ptr : 0;
     int n = 0;
-    const int out = FILL ? cnt_or_start[c] : 0;
-    for (int q0 = 0; q0 < Q; q0 += 32) {
-        const int q = q0 + lane;
-        bool nb = false;
-        if (q < Q) {
-            const int sc = src_cell[q];
-            const int sa = sc & 1023, sb = (sc >> 10) & 1023, sd = (sc >> 20) & 1023;
-            nb = (abs(sa - a) <= 1) && (abs(sb - b) <= 1) && (abs(sd - d) <= 1);
-        }
-        const unsigned m = __ballot_sync(KMC_FULL_MASK, nb);
-        if (FILL && nb) lists[out + n + __popc(m & ((1u << lane) - 1u))] = q;
-        n += __popc(m);
+    if (c < ncell && cell_max[c] >= row_lo && cell_min[c] < row_hi) {
+        int a = c / (ny * nz), b = (c / nz) % ny, d = c % nz;
+        for (int da = -1; da <= 1; ++da)
+            for (int db = -1; db <= 1; ++db)
+                for (int dd = -1; dd <= 1; ++dd) {
+                    int aa = a + da, bb = b + db, ee = d + dd;
+                    if (aa < 0 || aa >= nx || bb < 0 || bb >= ny || ee < 0 || ee >= nz) continue;
+                    int cc = (aa * ny + bb) * nz + ee;
+                    n += cstart[cc + 1] - cstart[cc];
+                }
     }
-    if (!FILL && lane == 0) cnt_or_start[c] = n;
+    cnt[c] = n;
+    if (n > 0) atomicMax(max_cnt, n);
+}
+
+__global__ void __launch_bounds__(128) nbr_fill_sort_kernel(int nx, int ny, int nz, const int *__restrict__ cstart,
+                                                           const int *__restrict__ src_by_cell,
+                                                           const int *__restrict__ list_start,
+                                                           int *__restrict__ lists) {
+    extern __shared__ int keys[];
+    __shared__ int seg_start[28];
+    const int c = blockIdx.x;
+    const int m = list_start[c + 1] - list_start[c];
+    if (m == 0) return;
+    const int a = c / (ny * nz), b = (c / nz) % ny, d = c % nz;
+    if (threadIdx.x == 0) {
+        int acc = 0, s = 0;
+        for (int da = -1; da <= 1; ++da)
+            for (int db = -1; db <= 1; ++db)
+                for (int dd = -1; dd <= 1; ++dd) {
+                    int aa = a + da, bb = b + db, ee = d + dd;
+                    seg_start[s++] = acc;
+                    if (aa < 0 || aa >= nx || bb < 0 || bb >= ny || ee < 0 || ee >= nz) continue;
+                    int cc = (aa * ny + bb) * nz + ee;
+                    acc += cstart[cc + 1] - cstart[cc];
+                }
+        seg_start[27] = acc;
+    }
+    __syncthreads();
+    {
+        int s = 0;
+        for (int da = -1; da <= 1; ++da)
+            for (int db = -1; db <= 1; ++db)
+                for (int dd = -1; dd <= 1; ++dd, ++s) {
+                    int len = seg_start[s + 1] - seg_start[s];
+                    if (len == 0) continue;
+                    int cc = ((a + da) * ny + (b + db)) * nz + (d + dd);
+                    const int *from = src_by_cell + cstart[cc];
+                    for (int i = threadIdx.x; i < len; i += blockDim.x) keys[seg_start[s] + i] = from[i];
+                }
+    }
+    int n2 = 1;
+    while (n2 < m) n2 <<= 1;
+    for (int i = m + threadIdx.x; i < n2; i += blockDim.x) keys[i] = 0x7fffffff;
+    __syncthreads();
+    for (int k = 2; k <= n2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+                int ixj = i ^ j;
+                if (ixj > i) {
+                    int va = keys[i], vb = keys[ixj];
+                    bool up = ((i & k) == 0);
+                    if ((va > vb) == up) { keys[i] = vb; keys[ixj] = va; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    int *out = lists + list_start[c];
+    for (int i = threadIdx.x; i < m; i += blockDim.x) out[i] = keys[i];
+}
+
+__global__ void cell_minmax_kernel(const int *__restrict__ site_cell, int N, int *__restrict__ cell_min,
+                                   int *__restrict__ cell_max) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    int c = site_cell[i];
+    atomicMin(cell_min + c, i);
+    atomicMax(cell_max + c, i);
 }
 
 constexpr int CT = 128;    // target sites per CTA
@@ -219,6 +285,8 @@ struct CoulombPlan {
     int ncell = 0, nblocks = 0;
     int *site_cell = nullptr, *cell_tstart = nullptr, *titems = nullptr, *blk_start = nullptr, *blk_cell = nullptr;
     int *list_start = nullptr;  // ncell+1 (per step)
+    int *cell_min = nullptr, *cell_max = nullptr;  // smallest / largest site id of a cell (static)
+    int *src_cstart = nullptr, *src_fill = nullptr;  // ncell+1 each (per step)
 };
 static CoulombPlan g_plan[16];  // per device
 
@@ -228,7 +296,7 @@ static int build_plan(kmcb200_ctx *ctx, CoulombPlan &P, int N, const double *x, 
     if (P.site_cell) {
         KMC_CUDA(cudaStreamSynchronize(ctx->stream));
         cudaFree(P.site_cell); cudaFree(P.cell_tstart); cudaFree(P.titems); cudaFree(P.blk_start); cudaFree(P.blk_cell);
-        cudaFree(P.list_start);
+        cudaFree(P.list_start); cudaFree(P.cell_min); cudaFree(P.cell_max); cudaFree(P.src_cstart); cudaFree(P.src_fill);
         P = CoulombPlan();
     }
     CellGridDev g;
@@ -243,10 +311,18 @@ static int build_plan(kmcb200_ctx *ctx, CoulombPlan &P, int N, const double *x, 
     KMC_CUDA(cudaMalloc(&P.titems, (size_t)N * sizeof(int)));
     KMC_CUDA(cudaMalloc(&P.blk_start, (size_t)(ncell + 1) * sizeof(int)));
     KMC_CUDA(cudaMalloc(&P.list_start, (size_t)(ncell + 1) * sizeof(int)));
+    KMC_CUDA(cudaMalloc(&P.cell_min, (size_t)(ncell + 1) * sizeof(int)));
+    KMC_CUDA(cudaMalloc(&P.cell_max, (size_t)(ncell + 1) * sizeof(int)));
+    KMC_CUDA(cudaMalloc(&P.src_cstart, (size_t)(ncell + 1) * sizeof(int)));
+    KMC_CUDA(cudaMalloc(&P.src_fill, (size_t)(ncell + 1) * sizeof(int)));
+    KMC_CUDA(cudaMemsetAsync(P.cell_min, 0x7f, (size_t)(ncell + 1) * sizeof(int), ctx->stream));
+    KMC_CUDA(cudaMemsetAsync(P.cell_max, 0xff, (size_t)(ncell + 1) * sizeof(int), ctx->stream));
     KMC_CUDA(cudaMemcpyAsync(P.cell_tstart, g.cell_start, (size_t)(ncell + 1) * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
     KMC_CUDA(cudaMemcpyAsync(P.titems, g.items, (size_t)N * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
     kmc_count_launch();
     site_cell_kernel<<<(N + 255) / 256, 256, 0, ctx->stream>>>(g, x, y, z, N, P.site_cell);
+    kmc_count_launch();
+    cell_minmax_kernel<<<(N + 255) / 256, 256, 0, ctx->stream>>>(P.site_cell, N, P.cell_min, P.cell_max);
     kmc_count_launch();
     cell_blocks_kernel<<<(ncell + 1 + 255) / 256, 256, 0, ctx->stream>>>(P.cell_tstart, ncell, CT, P.blk_start);
     KMC_CUDA(cudaGetLastError());
@@ -282,7 +358,7 @@ extern "C" int kmcb200_poisson_gridless(kmcb200_ctx *ctx, int N, const double *x
     unsigned long long *csum = nullptr;
     KMC_TRY(kmc_scratch(ctx, 6, (size_t)(N + 1) * sizeof(int), (void **)&offs));
     KMC_TRY(kmc_scratch(ctx, 10, 64, (void **)&csum));
-    KMC_CUDA(cudaMemsetAsync(csum, 0, 16, ctx->stream));
+    KMC_CUDA(cudaMemsetAsync(csum, 0, 32, ctx->stream));
     kmc_count_launch();
     pos_checksum_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(x, y, z, N, csum + 1);
     kmc_count_launch();
@@ -296,26 +372,52 @@ extern "C" int kmcb200_poisson_gridless(kmcb200_ctx *ctx, int N, const double *x
     unsigned long long checksum = *(unsigned long long *)((char *)ctx->h_mail + 8);
     KMC_TRY(build_plan(ctx, P, N, x, y, z, cutoff_radius, checksum));
     KMC_TRY(kmc_scratch(ctx, 7, (size_t)(Q + 1) * sizeof(Source), (void **)&src));
-    KMC_TRY(kmc_scratch(ctx, 8, (size_t)(Q + 1) * sizeof(int), (void **)&src_cell));
+    KMC_TRY(kmc_scratch(ctx, 8, (size_t)(2 * Q + 2) * sizeof(int), (void **)&src_cell));
+    int *src_by_cell = src_cell + Q + 1;
+    KMC_CUDA(cudaMemsetAsync(P.src_cstart, 0, (size_t)(P.ncell + 1) * sizeof(int), ctx->stream));
+    KMC_CUDA(cudaMemsetAsync(P.src_fill, 0, (size_t)(P.ncell + 1) * sizeof(int), ctx->stream));
     kmc_count_launch();
-    charged_scatter_kernel<<<(N + 255) / 256, 256, 0, ctx->stream>>>(charge, element, x, y, z, N, offs, P.site_cell, P.g.ny,
-                                                                    P.g.nz, src, src_cell);
+    charged_scatter_kernel<<<(N + 255) / 256, 256, 0, ctx->stream>>>(charge, element, x, y, z, N, offs, P.site_cell, src,
+                                                                    src_cell, P.src_cstart);
     KMC_CUDA(cudaGetLastError());
-    // 2. per-cell neighbourhood source lists (count, scan, fill)
-    unsigned cb = (unsigned)(((long long)(P.ncell + 1) * 32 + 127) / 128);  // one warp per cell
+    // 2. bin the sources by cell, then the sorted 27-cell neighbourhood list of every cell that holds requested targets
+    KMC_TRY(kmc_exclusive_scan_i32(ctx, P.src_cstart, P.src_cstart, (long long)P.ncell + 1, 4));
+    if (Q > 0) {
+        kmc_count_launch();
+        src_bin_fill_kernel<<<(Q + 255) / 256, 256, 0, ctx->stream>>>(Q, src_cell, P.src_cstart, P.src_fill, src_by_cell);
+    }
+    int *d_max = (int *)(csum + 2);
+    KMC_CUDA(cudaMemsetAsync(d_max, 0, sizeof(int), ctx->stream));
     kmc_count_launch();
-    cell_sources_kernel<false><<<cb, 128, 0, ctx->stream>>>(P.g.nx, P.g.ny, P.g.nz, src_cell, offs + N, P.cell_tstart,
-                                                           P.list_start, nullptr);
+    nbr_count_kernel<<<(P.ncell + 1 + 255) / 256, 256, 0, ctx->stream>>>(P.g.nx, P.g.ny, P.g.nz, P.src_cstart, P.cell_min,
+                                                                        P.cell_max, row_start, row_start + row_count,
+                                                                        P.list_start, d_max);
     KMC_CUDA(cudaGetLastError());
     KMC_TRY(kmc_exclusive_scan_i32(ctx, P.list_start, P.list_start, (long long)P.ncell + 1, 4));
     KMC_CUDA(cudaMemcpyAsync(ctx->h_mail, P.list_start + P.ncell, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    KMC_CUDA(cudaMemcpyAsync((char *)ctx->h_mail + 8, d_max, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     KMC_CUDA(cudaStreamSynchronize(ctx->stream));
     int total = *(int *)ctx->h_mail;
+    int max_nbr = *(int *)((char *)ctx->h_mail + 8);
     KMC_TRY(kmc_scratch(ctx, 9, (size_t)(total + 1) * sizeof(int), (void **)&lists));
-    kmc_count_launch();
-    cell_sources_kernel<true><<<cb, 128, 0, ctx->stream>>>(P.g.nx, P.g.ny, P.g.nz, src_cell, offs + N, P.cell_tstart,
-                                                          P.list_start, lists);
-    KMC_CUDA(cudaGetLastError());
+    if (total > 0) {
+        int n2 = 1;
+        while (n2 < max_nbr) n2 <<= 1;
+        size_t dyn = (size_t)n2 * sizeof(int);
+        if (dyn > 200 * 1024) {
+            kmc_set_error("Coulomb sum: %d charged sources around one 20 A cell exceed the shared-memory sort capacity", max_nbr);
+            return KMCB200_E_CAPACITY;
+        }
+        static size_t configured = 48 * 1024;
+        if (dyn > configured) {
+            KMC_CUDA(cudaFuncSetAttribute(nbr_fill_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            configured = dyn;
+        }
+        kmc_count_launch();
+        nbr_fill_sort_kernel<<<P.ncell, 128, dyn, ctx->stream>>>(P.g.nx, P.g.ny, P.g.nz, P.src_cstart, src_by_cell, P.list_start,
+                                                               lists);
+        KMC_CUDA(cudaGetLastError());
+    }
     // 3. the pair sum
     unsigned long long *pairs = csum;  // csum[0] was zeroed above
     if (P.nblocks > 0) {
