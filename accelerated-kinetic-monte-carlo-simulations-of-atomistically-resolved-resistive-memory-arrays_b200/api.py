@@ -671,9 +671,20 @@ class DeviceKMC:
 
     def superstep(self, max_events: int = 0):
         s = self.s
+        torch = self.ctx.torch
+        if not hasattr(self, "_tev"):
+            self._tev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            self.field_ms_total = 0.0
+            self.events_ms_total = 0.0
+        self._tev[0].record()
         self.field_solve()
+        self._tev[1].record()
         et, ne = self.ev.execute_kmc_step(self.neigh, self.layer, s.T_bg, s.freq, s.sigma, s.k, self.x, self.y,
                                           self.z, self.pot_charge, self.element, self.charge, max_events)
+        self._tev[2].record()
+        self._tev[2].synchronize()   # (execute_kmc_step already synchronised to return the event time)
+        self.field_ms_total += self._tev[0].elapsed_time(self._tev[1])
+        self.events_ms_total += self._tev[1].elapsed_time(self._tev[2])
         self.kmc_time += et
         self.step_count += 1
         self.last_n_events = ne

@@ -214,17 +214,21 @@ def run_gpu(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     timed = []
+    sim.field_ms_total = 0.0
+    sim.events_ms_total = 0.0
     for _ in range(args.steps):
         et, ne = sim.superstep()
         timed.append((sim.last_cg_iterations, ne))
     e1.record()
+    field_ms = sim.field_ms_total / args.steps      # sharded part: charge + K assembly + PCG + Coulomb (+ all-gathers)
+    events_ms = sim.events_ms_total / args.steps    # replicated part: rate list + residence-time loop
     barrier()
     ms_total = e0.elapsed_time(e1)
     launches = kmc.launch_count() - launches0
     if world > 1:
-        tt = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+        tt = torch.tensor([ms_total, field_ms, events_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms_total = float(tt.item())
+        ms_total, field_ms, events_ms = (float(v) for v in tt.tolist())
     ms_per_step = ms_total / args.steps
     value = 1e3 / ms_per_step
 
@@ -340,6 +344,7 @@ def run_gpu(args):
                            "K_rows": int(sim.K.rows), "K_nnz": int(sim.K.nnz)},
                 "e2e": {"value": 1e3 / e2e_ms, "unit": "steps/s", "ms_per_step": e2e_ms,
                         "h2d_bytes_per_step": 8 * N, "d2h_bytes_per_step": 16 * N},
+                "field_solve_ms_per_step": field_ms, "events_ms_per_step": events_ms,
                 "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roof, "stages": stages,
                 "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
