@@ -262,7 +262,7 @@ __global__ void sum_kernel(double *__restrict__ a, const double *__restrict__ b,
 
 extern "C" int kmcb200_update_charge(kmcb200_ctx *ctx, const int *element, int *charge, const int *neigh, int N, int nn,
                                      const int *metals_host, int num_metals, int row_start, int row_count) {
-    KMC_CHECK_ARG(ctx && element && charge && neigh, "null pointer");
+    KMC_CHECK_ARG(ctx && element && charge && (neigh || row_count == 0), "null pointer");
     KMC_CHECK_ARG(row_start >= 0 && row_count >= 0 && row_start + row_count <= N, "row range");
     KMC_CHECK_ARG(num_metals >= 0 && num_metals <= KMCB200_MAX_METALS && (num_metals == 0 || metals_host), "metals");
     unsigned metal_mask = 0;

@@ -243,9 +243,10 @@ int kmc_build_cellgrid(kmcb200_ctx *ctx, const double *x, const double *y, const
 extern "C" int kmcb200_compute_neighbor_list(kmcb200_ctx *ctx, int N, const double *x, const double *y,
                                              const double *z, double nn_dist, int nn, int row_start, int row_count,
                                              int *neigh_out) {
-    KMC_CHECK_ARG(ctx && x && y && z && neigh_out, "null pointer");
+    KMC_CHECK_ARG(ctx && x && y && z && (neigh_out || row_count == 0), "null pointer");
     KMC_CHECK_ARG(N > 0 && nn > 0 && nn <= MAX_NN, "N > 0, 0 < nn <= 64");
     KMC_CHECK_ARG(row_start >= 0 && row_count >= 0 && row_start + row_count <= N, "row range");
+    if (row_count == 0) return 0;
     CellGridDev g;
     KMC_TRY(kmc_build_cellgrid(ctx, x, y, z, 0, N, nn_dist, 0, nullptr, &g));
     kmc_count_launch();

@@ -349,3 +349,74 @@ def test_cpp_host_driver_reproduces_golden_output(kmc, tmp_path):
     with gzip.open(os.path.join(GOLD, "5nm_device", "snapshot_init.xyz.gz"), "rt") as f:
         ginit = f.read().split("\n")
     assert init[:37652] == ginit[:37652]   # byte-identical initial snapshot (same ostream formatting)
+
+
+# ---------------------------------------------------------------- edge cases
+def test_edge_empty_ranges_and_bad_arguments(kmc, ctx, s_small):
+    s = s_small
+    x, y, z, el = ctx.dev_d(s.x), ctx.dev_d(s.y), ctx.dev_d(s.z), ctx.dev_i(s.element)
+    # empty row ranges are no-ops
+    assert ctx.compute_neighbor_list(x, y, z, 3.5, 52, 10, 0).shape == (0, 52)
+    ch = ctx.empty_i(s.N, 7)
+    nb = ctx.compute_neighbor_list(x, y, z)
+    ctx.update_charge(el, ch, nb[:0], s.metals, row_start=5, row_count=0)
+    assert (to_np(ch) == 7).all()
+    pot = ctx.empty_d(s.N, 3.0)
+    ctx.poisson_gridless(x, y, z, el, ch, s.sigma, s.k, pot, row_start=0, row_count=0)
+    assert (to_np(pot) == 3.0).all()
+    # invalid arguments come back as errors with a message, never as a crash
+    with pytest.raises(kmc.KMCB200Error, match="row range"):
+        ctx.compute_neighbor_list(x, y, z, 3.5, 52, s.N - 1, 5)
+    with pytest.raises(kmc.KMCB200Error, match="nn"):
+        ctx.compute_neighbor_list(x, y, z, 3.5, 65)
+    with pytest.raises(kmc.KMCB200Error):
+        ctx.initialize_sparsity_K(x, y, z, s.lattice, 0, 3.5, s.N, s.N)       # no interior rows
+    K = ctx.initialize_sparsity_K(x, y, z, s.lattice, 0, 3.5, s.N_left, s.N_right)
+    with pytest.raises(kmc.KMCB200Error, match="do not match"):
+        ctx.assemble_K(K, s.N - 1, s.N_left, s.N_right, el, ch, s.metals, 1.0, 1.0, 1e-8)
+    K.close()
+
+
+def test_edge_no_possible_events_and_zero_bias(kmc, ctx, orc):
+    """a device without vacancies / ions / interstitial pairs has Psum = 0: the loop draws its two numbers, executes
+    nothing and returns an infinite residence time; Vd = 0 gives b = 0 and the PCG's 0/0 test stops at 0 iterations."""
+    s = make_synthetic(kmc, seed=2)
+    s.element = np.where(np.isin(s.element, [kmc.VACANCY, kmc.OXYGEN_DEFECT, kmc.DEFECT]), kmc.Hf_EL, s.element).astype(np.int32)
+    s.Vd = 0.0
+    dev = kmc.DeviceKMC(s, ctx=ctx)
+    et, ne = dev.superstep()
+    assert ne == 1 and np.isinf(et) and et > 0
+    log, _ = dev.ev.log()
+    assert len(log) in (0, 1)
+    assert dev.last_cg_iterations == 0
+    assert (to_np(dev.pot_charge) == 0).all()
+    mt, pos = dev.ev.rng_get_state()
+    r = orc.Rng(1); r.next(); r.next()
+    mt2, pos2 = r.state()
+    assert pos == pos2 and (mt == mt2).all()      # exactly two draws were consumed
+
+
+def test_edge_ragged_sizes_pbc_and_small_nn(kmc, ctx, orc):
+    """row count not a multiple of 256, periodic K, nn < 52: full supersteps against the oracle"""
+    s = make_synthetic(kmc, nx=9, ny=5, nz=7, seed=4, pbc=1, vac=0.12)
+    assert (s.N - 2 * s.N_left) % 256 != 0
+    dev = kmc.DeviceKMC(s, ctx=ctx)
+    sim = orc.OracleSim(s)
+    K = dev.K.to_host()
+    assert (K["col"] == sim.sp["col"]).all() and (K["row_ptr"] == sim.sp["row_ptr"]).all()
+    for _ in range(4):
+        et, ne = dev.superstep(max_events=25)
+        # oracle superstep has no event cap: emulate with the staged calls
+        sim.charge = orc.update_charge(sim.element, sim.charge, sim.neigh, s.metals)
+        data, dinv, rhs = orc.assemble_K(s.N, s.N_left, s.N_right, sim.element, sim.charge, s.metals, sim.sp, s.Vd, s.high_G, s.low_G)
+        n = s.N - s.N_left - s.N_right
+        xo, _, it, _ = orc.pcg_jacobi(sim.sp["row_ptr"], sim.sp["col"], data, dinv, rhs, sim.pot_boundary[s.N_left:s.N_left + n], 1e-14 * n)
+        sim.pot_boundary[s.N_left:s.N_left + n] = xo
+        pot = orc.coulomb(s.x, s.y, s.z, sim.element, sim.charge, s.sigma, s.k) + sim.pot_boundary
+        typ, prob = orc.build_events(sim.neigh, s.layer, s.T_bg, s.freq, s.sigma, s.k, s.x, s.y, s.z, pot, sim.element, sim.charge, s.E)
+        r = orc.event_loop(sim.neigh, typ, prob, sim.element, sim.charge, s.freq, sim.rng, max_events=25)
+        sim.element, sim.charge = r["element"], r["charge"]
+        log, _ = dev.ev.log()
+        assert it == dev.last_cg_iterations and ne == r["n_events"] and (log == r["log"]).all()
+        assert (to_np(dev.pot_boundary)[s.N_left:s.N_left + n] == xo).all()
+        assert (to_np(dev.element) == sim.element).all()
