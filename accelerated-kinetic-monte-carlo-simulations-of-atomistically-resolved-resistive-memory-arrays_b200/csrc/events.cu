@@ -41,6 +41,9 @@ struct kmcb200_events {
     double *prob = nullptr;
     unsigned char *type = nullptr;
     double *rowsum = nullptr, *chunksum = nullptr, *supersum = nullptr;
+    // inclusive scan_256 prefixes kept next to the sums, so the selector compares instead of re-scanning:
+    // rowincl[256 c + t] over the rows of chunk c, chunkincl[256 s + t] over the chunks of super s (both padded)
+    double *rowincl = nullptr, *chunkincl = nullptr;
     int *rev = nullptr;  // N * REV_STRIDE
     unsigned *mt = nullptr;  // 624 words + pos
     int *log = nullptr;
@@ -130,6 +133,44 @@ __device__ __forceinline__ int warp_pick_256(const Scan256 &sc, const double v[8
     *prev = pv;
     return tsel;
 }
+// The same selection from STORED inclusive prefixes (inc = incl[8 lane .. 8 lane + 7]); the values themselves are only
+// needed when no prefix exceeds number (load_v fetches them then).
+template <class LoadV>
+__device__ __forceinline__ int warp_pick_incl(const double inc[8], double number, double *prev, LoadV load_v) {
+    int kfirst = 8;
+#pragma unroll
+    for (int k = 7; k >= 0; --k)
+        if (inc[k] > number) kfirst = k;
+    int tsel = -1;
+    unsigned bf = __ballot_sync(KMC_FULL_MASK, kfirst < 8);
+    if (bf) {
+        int l = __ffs(bf) - 1;
+        tsel = l * 8 + __shfl_sync(KMC_FULL_MASK, kfirst, l);
+    } else {
+        double v[8];
+        load_v(v);
+        int klast = -1;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (v[k] > 0.0) klast = k;
+        unsigned bl = __ballot_sync(KMC_FULL_MASK, klast >= 0);
+        if (bl) {
+            int l = 31 - __clz(bl);
+            tsel = l * 8 + __shfl_sync(KMC_FULL_MASK, klast, l);
+        }
+    }
+    double pv = 0.0;
+    if (tsel > 0) {
+        int pl = (tsel - 1) >> 3, pk = (tsel - 1) & 7;
+        double cand = inc[0];
+#pragma unroll
+        for (int k = 1; k < 8; ++k)
+            if (k == pk) cand = inc[k];
+        pv = __shfl_sync(KMC_FULL_MASK, cand, pl);
+    }
+    *prev = pv;
+    return tsel;
+}
 // butterfly row sum of the summation spec: lane l holds p[l] + p[l+32]
 __device__ __forceinline__ double warp_row_sum(double p0, double p1) { return kmc_warp_xor_sum(p0 + p1); }
 
@@ -192,7 +233,8 @@ __global__ void __launch_bounds__(256) build_rates_kernel(int N, int nn, const i
                                                          const int *__restrict__ element,
                                                          const int *__restrict__ charge, EvEnergies E,
                                                          double *__restrict__ prob, unsigned char *__restrict__ type,
-                                                         double *__restrict__ rowsum, double *__restrict__ chunksum) {
+                                                         double *__restrict__ rowsum, double *__restrict__ chunksum,
+                                                         double *__restrict__ rowincl) {
     __shared__ double rs[256];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int row0 = blockIdx.x * 256 + w * 32;
@@ -239,12 +281,15 @@ __global__ void __launch_bounds__(256) build_rates_kernel(int N, int nn, const i
         for (int k = 0; k < 8; ++k) sc.a[k] = rs[8 * lane + k];
         warp_scan_256(sc);
         if (lane == 0) chunksum[blockIdx.x] = sc.total;
+        double2 *dst2 = reinterpret_cast<double2 *>(rowincl + (size_t)blockIdx.x * 256 + 8 * lane);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dst2[k] = make_double2(scan_incl(sc, 2 * k), scan_incl(sc, 2 * k + 1));
     }
 }
 
 // one warp per super: scan_256 total of its 256 chunk sums
 __global__ void __launch_bounds__(32) super_sums_kernel(const double *__restrict__ chunksum, long long nchunk,
-                                                       double *__restrict__ supersum) {
+                                                       double *__restrict__ supersum, double *__restrict__ chunkincl) {
     const int lane = threadIdx.x;
     Scan256 sc;
 #pragma unroll
@@ -254,6 +299,8 @@ __global__ void __launch_bounds__(32) super_sums_kernel(const double *__restrict
     }
     warp_scan_256(sc);
     if (lane == 0) supersum[blockIdx.x] = sc.total;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) chunkincl[(size_t)blockIdx.x * 256 + 8 * lane + k] = scan_incl(sc, k);
 }
 
 // ---- MT19937 (std::mt19937) + libstdc++ generate_canonical<double,53> -----------------------------------
@@ -294,7 +341,7 @@ struct EvLoopArgs {
     const int *neigh;
     double *prob;
     unsigned char *type;
-    double *rowsum, *chunksum, *supersum;
+    double *rowsum, *chunksum, *supersum, *rowincl, *chunkincl;
     const int *rev;
     int *element, *charge;
     unsigned *mt_state;  // 624 + pos
@@ -307,6 +354,8 @@ struct EvLoopArgs {
     int chunks_in_smem;  // chunk sums cached in dynamic shared memory for the whole loop
     long long *phase_cycles;  // 16 counters (KMC_EV_PROFILE builds)
 };
+
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ bool smem_set_insert(int *table, int mask, int key) {
     // open addressing; returns true if key was not present.  table entries are -1 when empty.
@@ -367,8 +416,11 @@ __global__ void __launch_bounds__(EV_THREADS, 1) event_loop_kernel(EvLoopArgs a)
     long long t_last = clock64();
 #endif
     double *cs = a.chunks_in_smem ? cs_smem : a.chunksum;
-    if (a.chunks_in_smem)
+    double *ci = a.chunks_in_smem ? cs_smem + a.nchunk : a.chunkincl;  // inclusive prefixes of the chunk sums, per super
+    if (a.chunks_in_smem) {
         for (long long q = tid; q < a.nchunk; q += EV_THREADS) cs_smem[q] = a.chunksum[q];
+        for (long long q = tid; q < a.nsuper * 256; q += EV_THREADS) ci[q] = a.chunkincl[q];
+    }
     for (int q = tid; q < 624; q += EV_THREADS) mt[q] = a.mt_state[q];
     for (int q = tid; q < MAX_SUPER; q += EV_THREADS) {
         ss[q] = (q < a.nsuper) ? a.supersum[q] : 0.0;
@@ -418,36 +470,35 @@ __global__ void __launch_bounds__(EV_THREADS, 1) event_loop_kernel(EvLoopArgs a)
                 long long r = -1;
                 if (ts >= 0) {
                     number = number - prev;
-                    // ---- chunk level ----------------------------------------------------------------------
+                    // ---- chunk level: stored prefixes of super ts ---------------------------------------------
+                    double inc[8];
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        long long c = (long long)ts * 256 + 8 * lane + k;
-                        v[k] = (c < a.nchunk) ? cs[c] : 0.0;
-                        sc.a[k] = v[k];
-                    }
-                    warp_scan_256(sc);
-                    int tc = warp_pick_256(sc, v, number, &prev);
+                    for (int k = 0; k < 8; ++k) inc[k] = ci[(long long)ts * 256 + 8 * lane + k];
+                    int tc = warp_pick_incl(inc, number, &prev, [&](double *vv) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            long long c = (long long)ts * 256 + 8 * lane + k;
+                            vv[k] = (c < a.nchunk) ? cs[c] : 0.0;
+                        }
+                    });
                     EV_TICK(9);
                     if (tc >= 0) {
                         number = number - prev;
                         const long long chunk = (long long)ts * 256 + tc;
-                        // ---- row level ----------------------------------------------------------------------
+                        // ---- row level: stored prefixes of the chunk (one L2 round trip) ------------------------
                         const long long rbase = chunk * 256 + 8 * lane;
-                        if (rbase + 8 <= a.N) {
-                            const double2 *src2 = reinterpret_cast<const double2 *>(a.rowsum + rbase);
+                        {
+                            const double2 *src2 = reinterpret_cast<const double2 *>(a.rowincl + rbase);
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
                                 double2 t2 = src2[k];
-                                v[2 * k] = t2.x; v[2 * k + 1] = t2.y;
+                                inc[2 * k] = t2.x; inc[2 * k + 1] = t2.y;
                             }
-                        } else {
-#pragma unroll
-                            for (int k = 0; k < 8; ++k) v[k] = (rbase + k < a.N) ? a.rowsum[rbase + k] : 0.0;
                         }
+                        int tr = warp_pick_incl(inc, number, &prev, [&](double *vv) {
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) sc.a[k] = v[k];
-                        warp_scan_256(sc);
-                        int tr = warp_pick_256(sc, v, number, &prev);
+                            for (int k = 0; k < 8; ++k) vv[k] = (rbase + k < a.N) ? a.rowsum[rbase + k] : 0.0;
+                        });
                         EV_TICK(10);
                         if (tr >= 0) {
                             number = number - prev;
@@ -458,10 +509,14 @@ __global__ void __launch_bounds__(EV_THREADS, 1) event_loop_kernel(EvLoopArgs a)
                 if (r >= 0) {
                     // ---- slot level: lanes hold slots lane and lane+32; walk the non-zero slots in order --------
                     const long long base = r * (long long)nn;
+                    if (lane < 2) prefetch_l2(a.rev + (size_t)r * REV_STRIDE + 32 * lane);  // for the zero-out phase
                     double p0 = 0.0, p1 = 0.0;
                     int nb0 = -1, nb1 = -1, ty0 = KMCB200_NULL_EVENT, ty1 = KMCB200_NULL_EVENT;
                     if (lane < nn) { p0 = a.prob[base + lane]; nb0 = a.neigh[base + lane]; ty0 = a.type[base + lane]; }
                     if (lane + 32 < nn) { p1 = a.prob[base + lane + 32]; nb1 = a.neigh[base + lane + 32]; ty1 = a.type[base + lane + 32]; }
+                    // every candidate partner's reverse-index row starts its trip from DRAM now (the zero-out needs one)
+                    if (p0 > 0.0) { prefetch_l2(a.rev + (size_t)nb0 * REV_STRIDE); prefetch_l2(a.rev + (size_t)nb0 * REV_STRIDE + 32); }
+                    if (p1 > 0.0) { prefetch_l2(a.rev + (size_t)nb1 * REV_STRIDE); prefetch_l2(a.rev + (size_t)nb1 * REV_STRIDE + 32); }
                     unsigned m0 = __ballot_sync(KMC_FULL_MASK, p0 > 0.0), m1 = __ballot_sync(KMC_FULL_MASK, p1 > 0.0);
                     int seln = -1, lastn = -1;
                     double acc = 0.0;
@@ -562,6 +617,7 @@ __global__ void __launch_bounds__(EV_THREADS, 1) event_loop_kernel(EvLoopArgs a)
                 }
             }
             const int nd = n_rows, nc = n_chunks;
+            for (int q = tid; q < 1024; q += EV_THREADS) chunk_set[q] = -1;  // next use: the next event's Z phase
 #ifdef KMC_EV_PROFILE
             if (tid == 0) { ph[14] += nd; ph[15] += nc; }
 #endif
@@ -577,45 +633,44 @@ __global__ void __launch_bounds__(EV_THREADS, 1) event_loop_kernel(EvLoopArgs a)
             }
             __syncthreads();
             EV_TICK(2);
-            // =============================== R2: chunk sums, one warp per touched chunk ==============================
+            // =============================== R2: one warp per touched chunk: scan_256 of its 256 row sums; the total goes
+            // to the chunk sums, the inclusive prefixes to rowincl (what the selector's row level compares against) ======
             for (int q = warp; q < nc; q += NW) {
                 const int c = chunk_list[q];
                 Scan256 sc;
-                const long long rbase = (long long)c * 256 + 8 * lane;
-                if (rbase + 8 <= a.N) {
-                    const double2 *src2 = reinterpret_cast<const double2 *>(a.rowsum + rbase);
+                const double2 *src2 = reinterpret_cast<const double2 *>(a.rowsum + (long long)c * 256 + 8 * lane);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) { double2 t2 = src2[k]; sc.a[2 * k] = t2.x; sc.a[2 * k + 1] = t2.y; }
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) sc.a[k] = (rbase + k < a.N) ? a.rowsum[rbase + k] : 0.0;
-                }
+                for (int k = 0; k < 4; ++k) { double2 t2 = src2[k]; sc.a[2 * k] = t2.x; sc.a[2 * k + 1] = t2.y; }
                 warp_scan_256(sc);
                 if (lane == 0) {
                     cs[c] = sc.total;
                     if (a.chunks_in_smem) a.chunksum[c] = sc.total;
                 }
+                double2 *dst2 = reinterpret_cast<double2 *>(a.rowincl + (long long)c * 256 + 8 * lane);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) dst2[k] = make_double2(scan_incl(sc, 2 * k), scan_incl(sc, 2 * k + 1));
             }
             __syncthreads();
             EV_TICK(4);
-            // =============================== U: super sums, one warp per touched super ==============================
+            // =============================== U: one warp per touched super: scan_256 of its chunk sums ===============
             const int nsd = n_supers;
             for (int q = warp; q < nsd; q += NW) {
                 const int sidx = super_list[q];
-                Scan256 sc;
+                Scan256 su;
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     long long c = (long long)sidx * 256 + 8 * lane + k;
-                    sc.a[k] = (c < a.nchunk) ? cs[c] : 0.0;
+                    su.a[k] = (c < a.nchunk) ? cs[c] : 0.0;
                 }
-                warp_scan_256(sc);
+                warp_scan_256(su);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) ci[(long long)sidx * 256 + 8 * lane + k] = scan_incl(su, k);
                 if (lane == 0) {
-                    ss[sidx] = sc.total;
-                    a.supersum[sidx] = sc.total;
+                    ss[sidx] = su.total;
+                    a.supersum[sidx] = su.total;
                     super_flag[sidx] = 0;
                 }
             }
-            for (int q = tid; q < 1024; q += EV_THREADS) chunk_set[q] = -1;
             __syncthreads();
             EV_TICK(3);
         }
@@ -663,9 +718,11 @@ extern "C" int kmcb200_events_create(kmcb200_ctx *ctx, int N, int nn, const int 
     auto A = [&](void **p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
     A((void **)&ev->prob, (size_t)total * sizeof(double));
     A((void **)&ev->type, (size_t)total);
-    A((void **)&ev->rowsum, (size_t)N * sizeof(double));
+    A((void **)&ev->rowsum, (size_t)ev->nchunk * 256 * sizeof(double));  // padded to whole chunks (tail stays 0)
     A((void **)&ev->chunksum, (size_t)ev->nchunk * sizeof(double));
     A((void **)&ev->supersum, (size_t)MAX_SUPER * sizeof(double));
+    A((void **)&ev->rowincl, (size_t)ev->nchunk * 256 * sizeof(double));
+    A((void **)&ev->chunkincl, (size_t)ev->nsuper * 256 * sizeof(double));
     A((void **)&ev->mt, 640 * sizeof(unsigned));
     A((void **)&ev->log, (size_t)ev->log_cap * 4 * sizeof(int));
     A((void **)&ev->log_psum, (size_t)ev->log_cap * sizeof(double));
@@ -685,6 +742,7 @@ extern "C" int kmcb200_events_create(kmcb200_ctx *ctx, int N, int nn, const int 
         return KMCB200_E_CUDA;
     }
     cudaMemsetAsync(ev->rev, 0xff, (size_t)N * REV_STRIDE * sizeof(int), ctx->stream);
+    cudaMemsetAsync(ev->rowsum, 0, (size_t)ev->nchunk * 256 * sizeof(double), ctx->stream);
     cudaMemsetAsync(fill, 0, (size_t)(N + 2) * sizeof(int), ctx->stream);
     unsigned blocks = (unsigned)((total + 255) / 256);
     kmc_count_launch();
@@ -709,6 +767,7 @@ extern "C" int kmcb200_events_destroy(kmcb200_events *ev) {
     if (!ev) return 0;
     if (ev->ctx) cudaStreamSynchronize(ev->ctx->stream);
     cudaFree(ev->prob); cudaFree(ev->type); cudaFree(ev->rowsum); cudaFree(ev->chunksum); cudaFree(ev->supersum);
+    cudaFree(ev->rowincl); cudaFree(ev->chunkincl);
     cudaFree(ev->rev); cudaFree(ev->mt); cudaFree(ev->log); cudaFree(ev->log_psum);
     cudaFree(ev->result);
     delete ev;
@@ -786,10 +845,11 @@ extern "C" int kmcb200_build_event_list(kmcb200_ctx *ctx, kmcb200_events *ev, in
     build_rates_kernel<<<(unsigned)ev->nchunk, 256, 0, ctx->stream>>>(N, nn, neigh, site_layer, kT, freq, sigma, k, x, y,
                                                                      z, site_potential_charge, site_element,
                                                                      site_charge, ev->energies, ev->prob, ev->type,
-                                                                     ev->rowsum, ev->chunksum);
+                                                                     ev->rowsum, ev->chunksum, ev->rowincl);
     KMC_CUDA(cudaGetLastError());
     kmc_count_launch();
-    super_sums_kernel<<<(unsigned)ev->nsuper, 32, 0, ctx->stream>>>(ev->chunksum, ev->nchunk, ev->supersum);
+    super_sums_kernel<<<(unsigned)ev->nsuper, 32, 0, ctx->stream>>>(ev->chunksum, ev->nchunk, ev->supersum,
+                                                                     ev->chunkincl);
     KMC_CUDA(cudaGetLastError());
     return 0;
 }
@@ -805,6 +865,7 @@ extern "C" int kmcb200_execute_kmc_step(kmcb200_ctx *ctx, kmcb200_events *ev, in
     a.N = N; a.nn = nn; a.nchunk = ev->nchunk; a.nsuper = ev->nsuper;
     a.neigh = neigh; a.prob = ev->prob; a.type = ev->type;
     a.rowsum = ev->rowsum; a.chunksum = ev->chunksum; a.supersum = ev->supersum;
+    a.rowincl = ev->rowincl; a.chunkincl = ev->chunkincl;
     a.rev = ev->rev;
     a.element = site_element; a.charge = site_charge;
     a.mt_state = ev->mt;
@@ -816,13 +877,15 @@ extern "C" int kmcb200_execute_kmc_step(kmcb200_ctx *ctx, kmcb200_events *ev, in
 #ifdef KMC_EV_PROFILE
     KMC_TRY(kmc_scratch(ctx, 5, 16 * sizeof(long long), (void **)&a.phase_cycles));
 #endif
-    size_t dyn = (size_t)ev->nchunk * sizeof(double);
-    a.chunks_in_smem = dyn <= 160 * 1024 ? 1 : 0;  // up to ~5.2 M sites; larger devices read chunk sums from L2
+    // chunk sums + their stored prefixes live in shared memory when they fit (up to ~3.2 M sites); larger devices
+    // read them from L2
+    size_t dyn = (size_t)(ev->nchunk + ev->nsuper * 256) * sizeof(double);
+    a.chunks_in_smem = dyn <= 190 * 1024 ? 1 : 0;
     if (!a.chunks_in_smem) dyn = 0;
     static size_t configured = 0;
     if (dyn > configured) {
-        KMC_CUDA(cudaFuncSetAttribute(event_loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(160 * 1024)));
-        configured = 160 * 1024;
+        KMC_CUDA(cudaFuncSetAttribute(event_loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(190 * 1024)));
+        configured = 190 * 1024;
     }
     kmc_count_launch();
     event_loop_kernel<<<1, EV_THREADS, dyn, ctx->stream>>>(a);
