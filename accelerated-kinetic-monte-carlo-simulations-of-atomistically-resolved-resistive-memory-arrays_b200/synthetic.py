@@ -9,6 +9,8 @@ contact layers (src/potential_solver_gpu.cu:855-861).
   order="xsorted" : interior sites stably sorted by x (narrow halo for row-sharded solves); contacts stay first/last
   order="lex"     : interior sites sorted by (x, y, z) lexicographically, the scheme of the shipped file's crystalline
                     blocks (narrow halo AND neighbouring rows share neighbours)
+  order="brick[B]": interior sites grouped into cubes of edge B angstrom (default 12.5, about one 256-row chunk); the
+                    bandwidth-minimised layout the reference's 40 nm input (crossbar_40_bwmin.xyz) is named for
 """
 from __future__ import annotations
 
@@ -46,6 +48,19 @@ def tile_structure(base: Structure, ty: int, tz: int, order: str = "file", vacan
         n = len(x)
         interior = np.arange(NL, n - NR)
         perm = interior[np.lexsort((z[interior], y[interior], x[interior]))]
+        full = np.concatenate([np.arange(NL), perm, np.arange(n - NR, n)])
+        x, y, z, el = x[full], y[full], z[full], el[full]
+    elif order.startswith("brick"):
+        # bandwidth-minimising 3-D blocking (what the reference's crossbar_40_bwmin.xyz is for): interior sites grouped
+        # into cubes of edge B (default 12.5 A ~ 256 sites, one SpMV / event chunk), sites inside a cube in (x, y, z)
+        # lexicographic order; contacts stay first / last
+        B = float(order[5:]) if len(order) > 5 else 12.5
+        n = len(x)
+        interior = np.arange(NL, n - NR)
+        bx, by, bz = (np.floor(x[interior] / B), np.floor(y[interior] / B), np.floor(z[interior] / B))
+        # cubes ordered y-major (then z, then x): contiguous row blocks are slabs across the long lateral axis, so a
+        # row-sharded solve exchanges only the thin x-z interfaces
+        perm = interior[np.lexsort((z[interior], y[interior], x[interior], bx, bz, by))]
         full = np.concatenate([np.arange(NL), perm, np.arange(n - NR, n)])
         x, y, z, el = x[full], y[full], z[full], el[full]
     elif order != "file":

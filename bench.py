@@ -363,7 +363,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("KMC_BENCH_WORKLOAD", "standin8x8"))
+    ap.add_argument("--workload", default=os.environ.get("KMC_BENCH_WORKLOAD", "standin8x8_brick"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--write-counters", action="store_true", help="record per-step PCG/event counters for the CPU arm")
     args = ap.parse_args()
