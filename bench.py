@@ -78,8 +78,11 @@ def build_workload(kmc, name):
     order = order or "file"
     t = {"standin8x8": 8, "standin4x4": 4, "standin2x2": 2, "standin16x16": 16}[base]
     s = syn.crossbar_standin(PARAM_5NM, t, t, order=order, Vd=15.0, rnd_seed=32)
+    note = {"file": "site order 'file' (tile images site-major: the 5nm file's block structure, wide K bandwidth)",
+            "brick": "site order 'brick' (bandwidth-minimised: interior sites grouped in 12.5 A cubes, contacts "
+                     "first/last -- the layout the reference's crossbar_40_bwmin.xyz input is named for)"}
     return s, (f"40nm_crossbar stand-in: {t}x{t} lateral tiling of the shipped 5nm cell, N={s.N}, "
-               f"num_atoms_first_layer={s.N_left}, Vd=15, site order '{order}'")
+               f"num_atoms_first_layer={s.N_left}, Vd=15, " + note.get(order, f"site order '{order}'"))
 
 
 # ------------------------------------------------------------------------------------------------
