@@ -63,6 +63,7 @@ struct kmcb200_ctx {
     void *pair_counter_dev = nullptr;
     // dot/pcg workspace
     CgState *cg_state = nullptr;  // device
+    bool cg_done_stale = false;   // a PCG solve ended abnormally: CgState::done may still be set
     double *partials = nullptr;   // device, 2 * max chunks
     size_t partials_cap = 0;
 };

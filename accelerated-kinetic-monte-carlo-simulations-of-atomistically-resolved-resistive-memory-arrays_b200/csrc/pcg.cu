@@ -506,8 +506,11 @@ extern "C" int kmcb200_spmv_dot(kmcb200_ctx *ctx, kmcb200_kmat *K, const double 
     KMC_CHECK_ARG(K->comm != nullptr && K->comm->size == 1, "kmcb200_spmv_dot is a single-rank call");
     const int nchunks = (K->rows + CH - 1) / CH;
     KMC_TRY(ensure_cg_workspace(ctx, nchunks));
-    CgState *st = ctx->cg_state;
-    KMC_CUDA(cudaMemsetAsync(&st->done, 0, sizeof(int), ctx->stream));
+    CgState *st = ctx->cg_state;  // `done` is 0 outside a PCG solve ...
+    if (ctx->cg_done_stale) {     // ... unless one returned early with an error
+        KMC_CUDA(cudaMemsetAsync(&st->done, 0, sizeof(int), ctx->stream));
+        ctx->cg_done_stale = false;
+    }
     const int fuse = nchunks <= 1024 ? 1 : 0;
     const unsigned long long ds = ++K->comm->dot_seq;
     KMC_TRY(spmv_launch(ctx, K, x_local, y_local, true, fuse, ds));
@@ -558,6 +561,7 @@ extern "C" int kmcb200_pcg_jacobi(kmcb200_ctx *ctx, kmcb200_kmat *K, double *r_l
     h->tol2 = relative_tolerance * relative_tolerance;  // dist_conjugate_gradient.cpp:217
     h->max_it = max_iterations;
     h->done = 0;
+    ctx->cg_done_stale = true;  // until the normal exit below
     KMC_CUDA(cudaMemcpyAsync(st, h, sizeof(CgState), cudaMemcpyHostToDevice, ctx->stream));
     // A*x0 (:191), residual + preconditioned residual + both setup dots (:187-213)
     int buf = 0;
@@ -659,6 +663,9 @@ extern "C" int kmcb200_pcg_jacobi(kmcb200_ctx *ctx, kmcb200_kmat *K, double *r_l
                     C->rank, rows, 1e3 * pt[0] / pn, 1e3 * pt[1] / pn, 1e3 * pt[2] / pn, 1e3 * pgap / pn, pn, pt[0], pt[1], pt[2]);
         for (auto &e : pall) cudaEventDestroy(e);
     }
+    // leave the state ready for kmcb200_spmv_dot / kmcb200_dot (their kernels early-exit while `done` is set)
+    KMC_CUDA(cudaMemsetAsync(&st->done, 0, sizeof(int), ctx->stream));
+    ctx->cg_done_stale = false;
     if (iterations_host) *iterations_host = h_flags[3];
     return 0;
 }
