@@ -58,15 +58,16 @@ struct kmcb200_events {
 namespace {
 
 constexpr int REV_STRIDE = 64;  // max number of rows that list a given site (in-degree of the neighbour graph)
-// reverse neighbour index, fixed stride: rev[s*64 + q] = slot (r*nn + n) with neigh[r][n] == s, -1 padded
-__global__ void rev_fill_kernel(const int *__restrict__ neigh, long long total, int *__restrict__ fill,
+// reverse neighbour index, fixed stride: rev[s*64 + q] = (r << 6) | n for the slots (r, n) with neigh[r][n] == s,
+// -1 padded (r < 2^24, n < 64: no division in the event loop)
+__global__ void rev_fill_kernel(const int *__restrict__ neigh, long long total, int nn, int *__restrict__ fill,
                                 int *__restrict__ rev, int *__restrict__ overflow) {
     long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= total) return;
     int j = neigh[s];
     if (j >= 0) {
         int pos = atomicAdd(fill + j, 1);
-        if (pos < REV_STRIDE - 1) rev[(size_t)j * REV_STRIDE + pos] = (int)s;  // last entry stays free (-1)
+        if (pos < REV_STRIDE - 1) rev[(size_t)j * REV_STRIDE + pos] = (int)((s / nn) << 6) | (int)(s % nn);  // last entry stays free (-1)
         else atomicExch(overflow, 1);
     }
 }
@@ -393,8 +394,10 @@ __device__ __forceinline__ void rng_prefetch_pair(unsigned *mt, unsigned *mt_bac
 //      one spare thread applies the event to element/charge, another draws the residence time
 //   R  one warp per touched chunk: new sums of its touched rows + scan_256 of the chunk's 256 row sums (1 RT)
 //   U  one warp per touched super: scan_256 of its chunk sums (shared memory)
+// SMEM: chunk sums + their stored prefixes live in dynamic shared memory (both padded to whole supers with zeros).
+template <bool SMEM>
 __global__ void __launch_bounds__(EV_THREADS, 1) event_loop_kernel(EvLoopArgs a) {
-    extern __shared__ double cs_smem[];  // chunk sums (when they fit)
+    extern __shared__ double cs_smem[];  // [nsuper*256] chunk sums, then [nsuper*256] inclusive prefixes
     __shared__ unsigned mt[624];
     __shared__ double ss[MAX_SUPER];
     __shared__ int rows_list[MAX_DIRTY], chunk_list[MAX_DIRTY], super_list[MAX_SUPER];
@@ -415,11 +418,15 @@ __global__ void __launch_bounds__(EV_THREADS, 1) event_loop_kernel(EvLoopArgs a)
     long long ph[16] = {0};
     long long t_last = clock64();
 #endif
-    double *cs = a.chunks_in_smem ? cs_smem : a.chunksum;
-    double *ci = a.chunks_in_smem ? cs_smem + a.nchunk : a.chunkincl;  // inclusive prefixes of the chunk sums, per super
-    if (a.chunks_in_smem) {
-        for (long long q = tid; q < a.nchunk; q += EV_THREADS) cs_smem[q] = a.chunksum[q];
-        for (long long q = tid; q < a.nsuper * 256; q += EV_THREADS) ci[q] = a.chunkincl[q];
+    const int npad = (int)a.nsuper * 256;  // chunk arrays are padded to whole supers (tail = 0)
+    double *cs, *ci;                       // chunk sums / inclusive prefixes of the chunk sums per super
+    if (SMEM) {
+        cs = cs_smem;
+        ci = cs_smem + npad;
+        for (int q = tid; q < npad; q += EV_THREADS) { cs[q] = a.chunksum[q]; ci[q] = a.chunkincl[q]; }
+    } else {
+        cs = a.chunksum;
+        ci = a.chunkincl;
     }
     for (int q = tid; q < 624; q += EV_THREADS) mt[q] = a.mt_state[q];
     for (int q = tid; q < MAX_SUPER; q += EV_THREADS) {
@@ -467,26 +474,23 @@ __global__ void __launch_bounds__(EV_THREADS, 1) event_loop_kernel(EvLoopArgs a)
                 double prev;
                 int ts = (Psum > 0.0) ? warp_pick_256(sc, v, number, &prev) : -1;
                 EV_TICK(8);
-                long long r = -1;
+                int r = -1;  // all slot indices fit 32 bits: N * nn <= 16.7 M * 64 < 2^31
                 if (ts >= 0) {
                     number = number - prev;
                     // ---- chunk level: stored prefixes of super ts ---------------------------------------------
                     double inc[8];
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) inc[k] = ci[(long long)ts * 256 + 8 * lane + k];
+                    for (int k = 0; k < 8; ++k) inc[k] = ci[ts * 256 + 8 * lane + k];
                     int tc = warp_pick_incl(inc, number, &prev, [&](double *vv) {
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            long long c = (long long)ts * 256 + 8 * lane + k;
-                            vv[k] = (c < a.nchunk) ? cs[c] : 0.0;
-                        }
+                        for (int k = 0; k < 8; ++k) vv[k] = cs[ts * 256 + 8 * lane + k];
                     });
                     EV_TICK(9);
                     if (tc >= 0) {
                         number = number - prev;
-                        const long long chunk = (long long)ts * 256 + tc;
+                        const int chunk = ts * 256 + tc;
                         // ---- row level: stored prefixes of the chunk (one L2 round trip) ------------------------
-                        const long long rbase = chunk * 256 + 8 * lane;
+                        const int rbase = chunk * 256 + 8 * lane;
                         {
                             const double2 *src2 = reinterpret_cast<const double2 *>(a.rowincl + rbase);
 #pragma unroll
@@ -508,15 +512,15 @@ __global__ void __launch_bounds__(EV_THREADS, 1) event_loop_kernel(EvLoopArgs a)
                 }
                 if (r >= 0) {
                     // ---- slot level: lanes hold slots lane and lane+32; walk the non-zero slots in order --------
-                    const long long base = r * (long long)nn;
-                    if (lane < 2) prefetch_l2(a.rev + (size_t)r * REV_STRIDE + 32 * lane);  // for the zero-out phase
+                    const int base = r * nn;
+                    if (lane < 2) prefetch_l2(a.rev + r * REV_STRIDE + 32 * lane);  // for the zero-out phase
                     double p0 = 0.0, p1 = 0.0;
                     int nb0 = -1, nb1 = -1, ty0 = KMCB200_NULL_EVENT, ty1 = KMCB200_NULL_EVENT;
                     if (lane < nn) { p0 = a.prob[base + lane]; nb0 = a.neigh[base + lane]; ty0 = a.type[base + lane]; }
                     if (lane + 32 < nn) { p1 = a.prob[base + lane + 32]; nb1 = a.neigh[base + lane + 32]; ty1 = a.type[base + lane + 32]; }
                     // every candidate partner's reverse-index row starts its trip from DRAM now (the zero-out needs one)
-                    if (p0 > 0.0) { prefetch_l2(a.rev + (size_t)nb0 * REV_STRIDE); prefetch_l2(a.rev + (size_t)nb0 * REV_STRIDE + 32); }
-                    if (p1 > 0.0) { prefetch_l2(a.rev + (size_t)nb1 * REV_STRIDE); prefetch_l2(a.rev + (size_t)nb1 * REV_STRIDE + 32); }
+                    if (p0 > 0.0) { prefetch_l2(a.rev + nb0 * REV_STRIDE); prefetch_l2(a.rev + nb0 * REV_STRIDE + 32); }
+                    if (p1 > 0.0) { prefetch_l2(a.rev + nb1 * REV_STRIDE); prefetch_l2(a.rev + nb1 * REV_STRIDE + 32); }
                     unsigned m0 = __ballot_sync(KMC_FULL_MASK, p0 > 0.0), m1 = __ballot_sync(KMC_FULL_MASK, p1 > 0.0);
                     int seln = -1, lastn = -1;
                     double acc = 0.0;
@@ -535,8 +539,8 @@ __global__ void __launch_bounds__(EV_THREADS, 1) event_loop_kernel(EvLoopArgs a)
                     if (seln >= 0) {
                         ej = __shfl_sync(KMC_FULL_MASK, (seln < 32) ? nb0 : nb1, seln & 31);
                         ety = __shfl_sync(KMC_FULL_MASK, (seln < 32) ? ty0 : ty1, seln & 31);
-                        ei = (int)r;
-                        eslot = (int)(base + seln);
+                        ei = r;
+                        eslot = base + seln;
                     }
                 }
             }
@@ -578,20 +582,21 @@ __global__ void __launch_bounds__(EV_THREADS, 1) event_loop_kernel(EvLoopArgs a)
                 const int which = tid / REV_STRIDE, q = tid % REV_STRIDE;
                 const int s_site = which ? ej : ei;
                 if (q < nn) {
-                    long long sl = (long long)s_site * nn + q;
+                    const int sl = s_site * nn + q;
                     a.prob[sl] = 0.0;
                     a.type[sl] = KMCB200_NULL_EVENT;
                 }
-                int sl = a.rev[(size_t)s_site * REV_STRIDE + q];
+                const int packed = a.rev[s_site * REV_STRIDE + q];
                 int rr = -1;
-                if (sl >= 0) {
+                if (packed >= 0) {
+                    const int sl = (packed >> 6) * nn + (packed & 63);
                     // a slot that already holds rate 0 does not change its row: only rows that lose a non-zero rate need
                     // their sums repaired (their recomputed sums would be bit-identical anyway)
                     double oldp = a.prob[sl];
                     a.type[sl] = KMCB200_NULL_EVENT;
                     if (oldp != 0.0) {
                         a.prob[sl] = 0.0;
-                        rr = sl / nn;
+                        rr = packed >> 6;
                     }
                 } else if (q == REV_STRIDE - 1) {
                     rr = s_site;  // the event's own rows (their sums become 0)
@@ -625,7 +630,7 @@ __global__ void __launch_bounds__(EV_THREADS, 1) event_loop_kernel(EvLoopArgs a)
             // (duplicates in rows_list recompute the same value)
             for (int q = warp; q < nd; q += NW) {
                 const int rr = rows_list[q];
-                const long long pb = (long long)rr * nn;
+                const int pb = rr * nn;
                 double p0 = (lane < nn) ? a.prob[pb + lane] : 0.0;
                 double p1 = (lane + 32 < nn) ? a.prob[pb + lane + 32] : 0.0;
                 double sacc = warp_row_sum(p0, p1);
@@ -638,15 +643,15 @@ __global__ void __launch_bounds__(EV_THREADS, 1) event_loop_kernel(EvLoopArgs a)
             for (int q = warp; q < nc; q += NW) {
                 const int c = chunk_list[q];
                 Scan256 sc;
-                const double2 *src2 = reinterpret_cast<const double2 *>(a.rowsum + (long long)c * 256 + 8 * lane);
+                const double2 *src2 = reinterpret_cast<const double2 *>(a.rowsum + c * 256 + 8 * lane);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) { double2 t2 = src2[k]; sc.a[2 * k] = t2.x; sc.a[2 * k + 1] = t2.y; }
                 warp_scan_256(sc);
                 if (lane == 0) {
                     cs[c] = sc.total;
-                    if (a.chunks_in_smem) a.chunksum[c] = sc.total;
+                    if (SMEM) a.chunksum[c] = sc.total;
                 }
-                double2 *dst2 = reinterpret_cast<double2 *>(a.rowincl + (long long)c * 256 + 8 * lane);
+                double2 *dst2 = reinterpret_cast<double2 *>(a.rowincl + c * 256 + 8 * lane);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) dst2[k] = make_double2(scan_incl(sc, 2 * k), scan_incl(sc, 2 * k + 1));
             }
@@ -658,13 +663,10 @@ __global__ void __launch_bounds__(EV_THREADS, 1) event_loop_kernel(EvLoopArgs a)
                 const int sidx = super_list[q];
                 Scan256 su;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    long long c = (long long)sidx * 256 + 8 * lane + k;
-                    su.a[k] = (c < a.nchunk) ? cs[c] : 0.0;
-                }
+                for (int k = 0; k < 8; ++k) su.a[k] = cs[sidx * 256 + 8 * lane + k];
                 warp_scan_256(su);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) ci[(long long)sidx * 256 + 8 * lane + k] = scan_incl(su, k);
+                for (int k = 0; k < 8; ++k) ci[sidx * 256 + 8 * lane + k] = scan_incl(su, k);
                 if (lane == 0) {
                     ss[sidx] = su.total;
                     a.supersum[sidx] = su.total;
@@ -719,7 +721,7 @@ extern "C" int kmcb200_events_create(kmcb200_ctx *ctx, int N, int nn, const int 
     A((void **)&ev->prob, (size_t)total * sizeof(double));
     A((void **)&ev->type, (size_t)total);
     A((void **)&ev->rowsum, (size_t)ev->nchunk * 256 * sizeof(double));  // padded to whole chunks (tail stays 0)
-    A((void **)&ev->chunksum, (size_t)ev->nchunk * sizeof(double));
+    A((void **)&ev->chunksum, (size_t)ev->nsuper * 256 * sizeof(double));  // padded to whole supers (tail stays 0)
     A((void **)&ev->supersum, (size_t)MAX_SUPER * sizeof(double));
     A((void **)&ev->rowincl, (size_t)ev->nchunk * 256 * sizeof(double));
     A((void **)&ev->chunkincl, (size_t)ev->nsuper * 256 * sizeof(double));
@@ -743,10 +745,11 @@ extern "C" int kmcb200_events_create(kmcb200_ctx *ctx, int N, int nn, const int 
     }
     cudaMemsetAsync(ev->rev, 0xff, (size_t)N * REV_STRIDE * sizeof(int), ctx->stream);
     cudaMemsetAsync(ev->rowsum, 0, (size_t)ev->nchunk * 256 * sizeof(double), ctx->stream);
+    cudaMemsetAsync(ev->chunksum, 0, (size_t)ev->nsuper * 256 * sizeof(double), ctx->stream);
     cudaMemsetAsync(fill, 0, (size_t)(N + 2) * sizeof(int), ctx->stream);
     unsigned blocks = (unsigned)((total + 255) / 256);
     kmc_count_launch();
-    rev_fill_kernel<<<blocks, 256, 0, ctx->stream>>>(neigh, total, fill, ev->rev, fill + N + 1);
+    rev_fill_kernel<<<blocks, 256, 0, ctx->stream>>>(neigh, total, nn, fill, ev->rev, fill + N + 1);
     int ovf = 0;
     cudaMemcpyAsync(&ovf, fill + N + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
@@ -879,16 +882,16 @@ extern "C" int kmcb200_execute_kmc_step(kmcb200_ctx *ctx, kmcb200_events *ev, in
 #endif
     // chunk sums + their stored prefixes live in shared memory when they fit (up to ~3.2 M sites); larger devices
     // read them from L2
-    size_t dyn = (size_t)(ev->nchunk + ev->nsuper * 256) * sizeof(double);
+    size_t dyn = (size_t)(2 * ev->nsuper * 256) * sizeof(double);
     a.chunks_in_smem = dyn <= 190 * 1024 ? 1 : 0;
-    if (!a.chunks_in_smem) dyn = 0;
-    static size_t configured = 0;
-    if (dyn > configured) {
-        KMC_CUDA(cudaFuncSetAttribute(event_loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(190 * 1024)));
-        configured = 190 * 1024;
+    static bool configured = false;
+    if (a.chunks_in_smem && !configured) {
+        KMC_CUDA(cudaFuncSetAttribute(event_loop_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(190 * 1024)));
+        configured = true;
     }
     kmc_count_launch();
-    event_loop_kernel<<<1, EV_THREADS, dyn, ctx->stream>>>(a);
+    if (a.chunks_in_smem) event_loop_kernel<true><<<1, EV_THREADS, dyn, ctx->stream>>>(a);
+    else event_loop_kernel<false><<<1, EV_THREADS, 0, ctx->stream>>>(a);
     KMC_CUDA(cudaGetLastError());
     EvResult *h = (EvResult *)ctx->h_mail;
     KMC_CUDA(cudaMemcpyAsync(h, ev->result, sizeof(EvResult), cudaMemcpyDeviceToHost, ctx->stream));

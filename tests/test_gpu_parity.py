@@ -1,6 +1,7 @@
 """GPU parity: every stage of the hot path (through the C ABI) against the CPU oracle on the same inputs.
 Bit-exact for integer / index work; FP64 tolerances are written next to each check."""
 import gzip
+import importlib
 import json
 import os
 
@@ -420,3 +421,29 @@ def test_edge_ragged_sizes_pbc_and_small_nn(kmc, ctx, orc):
         assert it == dev.last_cg_iterations and ne == r["n_events"] and (log == r["log"]).all()
         assert (to_np(dev.pot_boundary)[s.N_left:s.N_left + n] == xo).all()
         assert (to_np(dev.element) == sim.element).all()
+
+
+def test_superstep_brick_ordered_standin_matches_oracle(kmc, ctx, orc):
+    """The bench workload family (synthetic.crossbar_standin, bandwidth-minimised 'brick' site order) at 1x1 tiles:
+    contacts stay first/last, 3 supersteps identical to the oracle (sparsity, PCG iteration count, events, potentials)."""
+    syn = importlib.import_module(kmc.__name__ + ".synthetic")
+    s = syn.crossbar_standin(os.path.join(GOLD, "5nm_device", "parameters.txt"), 1, 1, order="brick", Vd=5.0, rnd_seed=5)
+    s5 = kmc.load_structure(os.path.join(GOLD, "5nm_device", "parameters.txt"), apply_vacancies=False)
+    assert s.N == s5.N and s.N_left == s5.N_left
+    # same sites, permuted: contacts untouched, interior is a permutation
+    assert np.array_equal(s.x[:s.N_left], s5.x[:s.N_left]) and np.array_equal(s.x[-s.N_right:], s5.x[-s.N_right:])
+    key = lambda t: np.lexsort((t.z, t.y, t.x))
+    assert np.array_equal(s.x[key(s)], s5.x[key(s5)]) and np.array_equal(s.z[key(s)], s5.z[key(s5)])
+    dev = kmc.DeviceKMC(s, ctx=ctx)
+    sim = orc.OracleSim(s)
+    h = dev.K.to_host()
+    assert np.array_equal(h["row_ptr"], sim.sp["row_ptr"]) and np.array_equal(h["col"], sim.sp["col"])
+    for _ in range(3):
+        et, ne = dev.superstep()
+        log, psum = dev.ev.log()
+        r = sim.superstep()
+        assert ne == r["n_events"] and dev.last_cg_iterations == r["cg_iterations"]
+        assert (log[:, :3] == r["events"][:, :3]).all()
+        assert abs(et - r["event_time"]) <= 1e-12 * r["event_time"]
+    assert np.abs(to_np(dev.pot_charge) - sim.pot_total).max() <= 1e-10 * np.abs(sim.pot_total).max()
+    assert (to_np(dev.element) == sim.element).all() and (to_np(dev.charge) == sim.charge).all()
