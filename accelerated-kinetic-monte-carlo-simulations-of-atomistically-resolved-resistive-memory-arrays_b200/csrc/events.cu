@@ -884,6 +884,7 @@ extern "C" int kmcb200_execute_kmc_step(kmcb200_ctx *ctx, kmcb200_events *ev, in
     // read them from L2
     size_t dyn = (size_t)(2 * ev->nsuper * 256) * sizeof(double);
     a.chunks_in_smem = dyn <= 190 * 1024 ? 1 : 0;
+    if (getenv("KMCB200_EV_NO_SMEM")) a.chunks_in_smem = 0;  // tests: exercise the large-device (> 3.2 M sites) path
     static bool configured = false;
     if (a.chunks_in_smem && !configured) {
         KMC_CUDA(cudaFuncSetAttribute(event_loop_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(190 * 1024)));

@@ -447,3 +447,20 @@ def test_superstep_brick_ordered_standin_matches_oracle(kmc, ctx, orc):
         assert abs(et - r["event_time"]) <= 1e-12 * r["event_time"]
     assert np.abs(to_np(dev.pot_charge) - sim.pot_total).max() <= 1e-10 * np.abs(sim.pot_total).max()
     assert (to_np(dev.element) == sim.element).all() and (to_np(dev.charge) == sim.charge).all()
+
+
+def test_event_loop_large_device_path(kmc, ctx, orc, monkeypatch):
+    """Devices above ~3.2 M sites keep the chunk sums / stored prefixes in global memory instead of shared memory
+    (event_loop_kernel<false>); force that path on a small device and compare the event log with the oracle."""
+    monkeypatch.setenv("KMCB200_EV_NO_SMEM", "1")
+    s = make_synthetic(kmc, seed=21, vac=0.15)
+    dev = kmc.DeviceKMC(s, ctx=ctx)
+    sim = orc.OracleSim(s)
+    for _ in range(4):
+        et, ne = dev.superstep()
+        log, psum = dev.ev.log()
+        r = sim.superstep()
+        assert ne == r["n_events"] and dev.last_cg_iterations == r["cg_iterations"]
+        assert (log[:, :3] == r["events"][:, :3]).all()
+        assert abs(et - r["event_time"]) <= 1e-12 * r["event_time"]
+    assert (to_np(dev.element) == sim.element).all() and (to_np(dev.charge) == sim.charge).all()
