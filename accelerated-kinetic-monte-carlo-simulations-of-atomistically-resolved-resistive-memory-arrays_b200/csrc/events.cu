@@ -18,7 +18,6 @@
 
 namespace {
 constexpr int EV_THREADS = 512;
-constexpr int EV_GROUPS = EV_THREADS / 256;
 constexpr int MAX_DIRTY = 1024;
 constexpr int MAX_SUPER = 256;
 }  // namespace
@@ -99,7 +98,6 @@ __device__ __forceinline__ double scan_incl(const Scan256 &r, int k) {
 // first t (0..255) with incl[t] > number, else the last t with v[t] > 0, else -1; *prev = incl[t-1] (0 for t == 0).
 // v: the original values (before the scan).
 __device__ __forceinline__ int warp_pick_256(const Scan256 &sc, const double v[8], double number, double *prev) {
-    const int lane = threadIdx.x & 31;
     double inc[8];
     int kfirst = 8, klast = -1;
 #pragma unroll
@@ -388,12 +386,17 @@ __device__ __forceinline__ void rng_prefetch_pair(unsigned *mt, unsigned *mt_bac
 }
 
 // The persistent event loop: ONE CTA.  Every phase issues all its global loads together, so a phase costs about
-// one L2/DRAM round trip; 4 block barriers per event:
-//   S  warp 0 (selector, warp-synchronous): top -> chunk -> row (1 RT) -> slot (1 RT); publishes (i, j, type)
-//   Z  all warps: zero-out through the fixed-stride reverse index (1 RT) + list of touched rows / unique chunks;
-//      one spare thread applies the event to element/charge, another draws the residence time
-//   R  one warp per touched chunk: new sums of its touched rows + scan_256 of the chunk's 256 row sums (1 RT)
-//   U  one warp per touched super: scan_256 of its chunk sums (shared memory)
+// one L2/DRAM round trip; 5 block barriers per event:
+//   S   warp 0 (selector, warp-synchronous): top level = scan_256 of the super sums; chunk and row level = compare
+//       against the STORED inclusive prefixes (chunkincl in shared memory, rowincl: 1 RT); slot level = ordered walk
+//       over the row's non-zero slots (1 RT); publishes (i, j, type); prefetches the reverse-index rows of i and of
+//       every candidate j into L2.  Warp 1 meanwhile draws the uniforms of the NEXT event.
+//   Z   all warps: zero-out through the fixed-stride reverse index (1 RT + 1 RT) + list of touched rows / unique
+//       chunks / supers; one spare thread applies the event to element/charge, another draws the residence time
+//   R1  one warp per touched row: butterfly row sum (1 RT)
+//   R2  one warp per touched chunk: scan_256 of its 256 row sums (1 RT) -> chunk sum + the chunk's stored prefixes
+//   U   one warp per touched super: scan_256 of its chunk sums (shared memory) -> super sum + stored prefixes
+// Measured budget and the building-block latencies: DESIGN.md section 3 ("Events").
 // SMEM: chunk sums + their stored prefixes live in dynamic shared memory (both padded to whole supers with zeros).
 template <bool SMEM>
 __global__ void __launch_bounds__(EV_THREADS, 1) event_loop_kernel(EvLoopArgs a) {
