@@ -690,6 +690,20 @@ class DeviceKMC:
         self.last_n_events = ne
         return et, ne
 
+    def snapshot(self):
+        """Mutable simulation state (site elements/charges, PCG warm start, generator, clocks): restoring it replays
+        the same supersteps bit for bit (the restart the reference gets from its snapshot files)."""
+        mt, pos = self.ev.rng_get_state()
+        return {"element": self.element.clone(), "charge": self.charge.clone(),
+                "pot_boundary": self.pot_boundary.clone(), "pot_charge": self.pot_charge.clone(),
+                "mt": mt.copy(), "pos": int(pos), "kmc_time": self.kmc_time, "step_count": self.step_count}
+
+    def restore(self, snap):
+        self.element.copy_(snap["element"]); self.charge.copy_(snap["charge"])
+        self.pot_boundary.copy_(snap["pot_boundary"]); self.pot_charge.copy_(snap["pot_charge"])
+        self.ev.rng_set_state(snap["mt"], snap["pos"])
+        self.kmc_time, self.step_count = snap["kmc_time"], snap["step_count"]
+
     def run(self, t_switch: Optional[float] = None, max_steps: Optional[int] = None):
         """while (kmc_time < t) superstep  (src/kmc_main.cpp:328); returns the per-step records"""
         t = self.s.t_switch if t_switch is None else t_switch
