@@ -137,11 +137,22 @@ def oracle_state(orc, s):
             "pot_boundary": np.zeros(s.N), "pot_total": np.zeros(s.N)}
 
 
+def use_all_host_threads():
+    """The CPU arm uses every host core it may run on.  torchrun exports OMP_NUM_THREADS=1 for its workers; the OpenMP
+    runtime of the oracle library reads the variable when it is loaded, so it is reset before the first import."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(n)
+
+
 def run_reference(args):
     """--impl reference: the oracle port timed on the host cores (no GPU), bounded sample per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    use_all_host_threads()
     kmc = importlib.import_module(PKG)
     from oracle import binding as orc
     s, desc = build_workload(kmc, args.workload)
@@ -326,6 +337,7 @@ def run_gpu(args):
     # ---- CPU baseline (rank 0, N = 1): the oracle port on the box's host cores, bounded sample -------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        use_all_host_threads()
         from oracle import binding as orc
         st = oracle_state(orc, s)
         st["element"] = sim.element.cpu().numpy()
