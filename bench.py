@@ -305,6 +305,7 @@ def run_gpu(args):
         roof = {"kernel": "spmv_kernel<8,DOT> (CSR SpMV with the p.Ap chunk partials fused; + dot_finalize)", "bound": "hbm",
                 "achieved": ach,
                 "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                "frac_of_nominal_8TBs": ach / 8000.0,   # report both denominators
                 "algorithmic_bytes_per_launch": spmv_bytes, "ms_per_launch": t_spmv}
         try:
             prof = json.load(open(os.path.join(ROOT, "profiles", "spmv_traffic.json")))
@@ -356,7 +357,9 @@ def run_gpu(args):
     if rank == 0:
         line = {"metric": "kmc_steps_per_sec", "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
-                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                # BASELINE.md publishes one number for this metric: ~87 KMC steps/s, steady state, shipped 5 nm device
+                "vs_baseline": (value / 87.0 if args.workload == "5nm" else None), "dtype": "f64",
+                "data": ("shipped structure" if args.workload == "5nm" else "synthetic"),
                 "config": {"workload": desc, "l2_policy": "inputs (matrix + event list) >> L2; no flush needed",
                            "cg_iterations_per_step": cg_per_step, "events_per_step": ev_per_step,
                            "warmup_counters": per_step, "setup_s": round(t_setup, 2),
