@@ -334,6 +334,12 @@ def run_gpu(args):
 
     cg_per_step = float(np.mean([c for c, _ in timed]))
     ev_per_step = float(np.mean([e for _, e in timed]))
+    if stages and cg_per_step > 0 and world == 1:
+        # one Jacobi-PCG iteration = SpMV + 11 vector streams (12 nnz + 108 n bytes); time derived from
+        # the timed supersteps: field solve minus the separately timed charge / assembly / Coulomb stages
+        pcg_ms = (field_ms - stages["update_charge_ms"] - stages["assemble_K_ms"] - stages["coulomb_ms"]) / cg_per_step
+        stages["pcg_iteration_ms"] = pcg_ms
+        stages["pcg_iteration_GBs"] = (12.0 * sim.K.nnz + 108.0 * sim.K.rows) / (pcg_ms * 1e-3) / 1e9
 
     # ---- CPU baseline (rank 0, N = 1): the oracle port on the box's host cores, bounded sample -------------------
     cpu = None
