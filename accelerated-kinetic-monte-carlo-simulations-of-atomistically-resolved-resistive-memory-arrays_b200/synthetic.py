@@ -23,6 +23,20 @@ from .api import Structure, assign_layers, layer_table, load_structure, make_sub
 PITCH = 51.15  # lateral pitch of the 5 nm cell [A]  (24 x 2.13125)
 
 
+def brick_permutation(x, y, z, n_left: int, n_right: int, B: float = 12.5) -> np.ndarray:
+    """Bandwidth-minimising 3-D blocking of the interior sites (what the reference's crossbar_40_bwmin.xyz is for):
+    interior sites are grouped into cubes of edge B angstrom (12.5 A ~ 256 sites, one SpMV / event chunk); cubes are
+    ordered y-major (then z, then x) so that contiguous row blocks are slabs across the long lateral axis and a
+    row-sharded solve exchanges only thin x-z interfaces; sites inside a cube in (x, y, z) lexicographic order.  The first
+    n_left and last n_right sites (the contact layers, src/potential_solver_gpu.cu:855-861) keep their places.
+    Returns the permutation `perm` with new_site[k] = old_site[perm[k]]."""
+    n = len(x)
+    interior = np.arange(n_left, n - n_right)
+    bx, by, bz = (np.floor(x[interior] / B), np.floor(y[interior] / B), np.floor(z[interior] / B))
+    perm = interior[np.lexsort((z[interior], y[interior], x[interior], bx, bz, by))]
+    return np.concatenate([np.arange(n_left), perm, np.arange(n - n_right, n)])
+
+
 def tile_structure(base: Structure, ty: int, tz: int, order: str = "file", vacancy_concentration: float = 0.05,
                    rnd_seed: int = 32, Vd: float | None = None) -> Structure:
     """ty x tz lateral tiling of a PRISTINE base cell, then Device::makeSubstoichiometric on the tiled device."""
@@ -51,17 +65,8 @@ def tile_structure(base: Structure, ty: int, tz: int, order: str = "file", vacan
         full = np.concatenate([np.arange(NL), perm, np.arange(n - NR, n)])
         x, y, z, el = x[full], y[full], z[full], el[full]
     elif order.startswith("brick"):
-        # bandwidth-minimising 3-D blocking (what the reference's crossbar_40_bwmin.xyz is for): interior sites grouped
-        # into cubes of edge B (default 12.5 A ~ 256 sites, one SpMV / event chunk), sites inside a cube in (x, y, z)
-        # lexicographic order; contacts stay first / last
         B = float(order[5:]) if len(order) > 5 else 12.5
-        n = len(x)
-        interior = np.arange(NL, n - NR)
-        bx, by, bz = (np.floor(x[interior] / B), np.floor(y[interior] / B), np.floor(z[interior] / B))
-        # cubes ordered y-major (then z, then x): contiguous row blocks are slabs across the long lateral axis, so a
-        # row-sharded solve exchanges only the thin x-z interfaces
-        perm = interior[np.lexsort((z[interior], y[interior], x[interior], bx, bz, by))]
-        full = np.concatenate([np.arange(NL), perm, np.arange(n - NR, n)])
+        full = brick_permutation(x, y, z, NL, NR, B)
         x, y, z, el = x[full], y[full], z[full], el[full]
     elif order != "file":
         raise ValueError(order)
