@@ -130,6 +130,22 @@ def cpu_step_cost(orc, s, state, cg_iters_per_step, events_per_step, coulomb_row
     return t
 
 
+def reference_cpu_coulomb(orc, s, charge, rows=64):
+    """SURVEY.md 8(d)(i): the reference's own surviving CPU code for the charge sum, Device::poisson_gridless
+    (src/potential_solver.cpp:74-94: OpenMP all-to-all, PBC-aware, no cutoff -- a timing baseline, not the live
+    algorithm), run through oracle/_ref (the reference's compiled site_dist / v_solve) on a bounded block of rows."""
+    lo = s.N // 2
+    t0 = time.perf_counter()
+    out = orc.ref_poisson_gridless_rows(s.x, s.y, s.z, charge, s.lattice, s.pbc, s.sigma, s.k, lo, lo + rows)
+    dt = time.perf_counter() - t0
+    if out is None:
+        return None
+    q = int(np.count_nonzero(charge))
+    return {"kind": "reference", "source": "Device::poisson_gridless, src/potential_solver.cpp:74-94 via oracle/_ref",
+            "rows_timed": rows, "seconds": dt, "charged_sites": q,
+            "extrapolated_seconds_per_step": dt * s.N / rows, "pair_evaluations_per_s": rows * q / dt if dt > 0 else None}
+
+
 def oracle_state(orc, s):
     neigh = orc.neighbor_list(s.x, s.y, s.z, 3.5, 52, use_cells=True)
     sp = orc.sparsity_K(s.x, s.y, s.z, s.lattice, s.pbc, s.nn_dist, s.N_left, s.N_right, use_cells=True)
@@ -176,7 +192,9 @@ def run_reference(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": desc, "per_step_counters": counters},
-            "cpu_baseline": {"value": val, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": val, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample,
+                             "reference_cpu_charge_sum": reference_cpu_coulomb(
+                                 orc, s, orc.update_charge(st["element"], st["charge"], st["neigh"], s.metals))},
             "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -353,12 +371,15 @@ def run_gpu(args):
         st["pot_total"] = sim.pot_charge.cpu().numpy()
         t = cpu_step_cost(orc, s, st, cg_per_step, ev_per_step)
         tot = sum(t.values())
+        ref_coul = reference_cpu_coulomb(orc, s, st["charge"] if np.count_nonzero(st["charge"]) else
+                                         orc.update_charge(st["element"], st["charge"], st["neigh"], s.metals))
         cpu = {"value": 1.0 / tot, "unit": "steps/s", "cores": orc.lib().orc_num_threads(), "kind": "port",
                "sample": (f"oracle port (the reference has no CPU code for this path): one superstep of the same workload "
                           f"from the post-timing state: full update_charge + full K assembly + PCG setup + "
                           f"{cg_per_step:.1f} PCG iterations (cost measured on 2) + Coulomb sum on 2/128 of the rows "
                           f"scaled to N + full rate list + {ev_per_step:.0f} events"),
-               "stage_seconds": {k: round(v, 4) for k, v in t.items()}}
+               "stage_seconds": {k: round(v, 4) for k, v in t.items()},
+               "reference_cpu_charge_sum": ref_coul}
 
     if rank == 0:
         line = {"metric": "kmc_steps_per_sec", "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,

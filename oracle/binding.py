@@ -307,4 +307,21 @@ def ref_lib():
     L.ref_rng_next.restype = C.c_double
     L.ref_site_dist.restype = C.c_double
     L.ref_v_solve.restype = C.c_double
+    if hasattr(L, "ref_poisson_gridless_rows"):
+        L.ref_poisson_gridless_rows.restype = C.c_double
     return L
+
+
+def ref_poisson_gridless_rows(x, y, z, charge, lattice, pbc, sigma, k, row_begin, row_end):
+    """The reference's CPU charge sum (Device::poisson_gridless, src/potential_solver.cpp:74-94) for rows
+    [row_begin, row_end), evaluated with the reference's own compiled site_dist / v_solve (oracle/_ref).
+    All-to-all, PBC-aware, no cutoff: a timing baseline, not the live algorithm.  Returns None without oracle/_ref."""
+    L = ref_lib()
+    if L is None or not hasattr(L, "ref_poisson_gridless_rows"):
+        return None
+    x, y, z, charge = _d(x), _d(y), _d(z), _i(charge)
+    lat = _d(np.asarray(lattice, dtype=np.float64))
+    out = np.zeros(max(row_end - row_begin, 0))
+    L.ref_poisson_gridless_rows(C.c_int(len(x)), _p(x), _p(y), _p(z), _p(charge), _p(lat), C.c_int(int(pbc)),
+                                C.c_double(sigma), C.c_double(k), C.c_int(row_begin), C.c_int(row_end), _p(out))
+    return out

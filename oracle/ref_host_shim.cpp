@@ -73,4 +73,31 @@ double ref_site_dist(double x1, double y1, double z1, double x2, double y2, doub
 }
 double ref_v_solve(double r, int charge, double sigma, double k, double q) { return v_solve(r, charge, sigma, k, q); }
 
+// The reference's surviving CPU implementation of the long-range charge sum, Device::poisson_gridless
+// (src/potential_solver.cpp:74-94): OpenMP over sites i, ALL sites j with a non-zero charge, PBC-aware site_dist, no
+// 20 A cutoff -- NOT numerically equivalent to the live GPU kernel, a timing baseline only.  Device itself
+// cannot be compiled here (its headers pull in ROCm/MPI), so the 10-line loop is driven from this shim over the
+// reference's own compiled site_dist() and v_solve() (src/utils.cpp).  Rows [row_begin, row_end) only: bounded sample.
+double ref_poisson_gridless_rows(int N, const double *x, const double *y, const double *z, const int *charge,
+                                 const double *lattice, int pbc, double sigma, double k, int row_begin, int row_end,
+                                 double *out) {
+    std::vector<double> l(lattice, lattice + 3);
+    double q = 1.60217663e-19;  // Device::q, src/Device.h:119 (v_solve takes non-const references)
+    double checksum = 0.0;
+#pragma omp parallel for reduction(+ : checksum) firstprivate(q, sigma, k)
+    for (int i = row_begin; i < row_end; i++) {
+        double V_temp = 0;
+        for (int j = 0; j < N; j++) {
+            if (i != j && charge[j] != 0) {
+                double r_dist = (1e-10) * site_dist(x[i], y[i], z[i], x[j], y[j], z[j], l, pbc != 0);
+                int qj = charge[j];
+                V_temp += v_solve(r_dist, qj, sigma, k, q);
+            }
+        }
+        out[i - row_begin] = V_temp;
+        checksum += V_temp;
+    }
+    return checksum;
+}
+
 }  // extern "C"

@@ -125,3 +125,30 @@ def test_layers_and_partition(kmc, s5):
         assert c.max() - c.min() <= 1 and (np.diff(c) <= 0).all()  # KMC_comm.h:249-263: the first n%P ranks get +1
         ca, da = kmc.partition(n, P, aligned=True)
         assert ca.sum() == n and ((da % 256 == 0) | (da == n)).all()
+
+
+def test_reference_cpu_charge_sum_matches_formula(orc):
+    """oracle/_ref drives the reference's surviving CPU charge sum (Device::poisson_gridless,
+    src/potential_solver.cpp:74-94) over the reference's own compiled site_dist / v_solve; check it against the
+    formula written out in numpy (non-periodic and periodic)."""
+    import math
+    if orc.ref_lib() is None:
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    rng = np.random.default_rng(0)
+    N = 80
+    L = [30.0, 25.0, 20.0]
+    x, y, z = rng.uniform(0, L[0], N), rng.uniform(0, L[1], N), rng.uniform(0, L[2], N)
+    q = rng.choice([0, 0, 2, -2], N).astype(np.int32)
+    sigma, k, e = 3.5e-10, 8.987552e9 / 23, 1.60217663e-19
+    for pbc in (0, 1):
+        out = orc.ref_poisson_gridless_rows(x, y, z, q, L, pbc, sigma, k, 7, 41)
+        ref = np.zeros(34)
+        for a, i in enumerate(range(7, 41)):
+            for j in range(N):
+                if i != j and q[j] != 0:
+                    dx, dy, dz = abs(x[i] - x[j]), abs(y[i] - y[j]), abs(z[i] - z[j])
+                    if pbc:  # site_dist, src/utils.cpp: minimum image in y and z only
+                        dy, dz = min(dy, L[1] - dy), min(dz, L[2] - dz)
+                    r = 1e-10 * math.sqrt(dx * dx + dy * dy + dz * dz)
+                    ref[a] += q[j] * math.erfc(r / (sigma * math.sqrt(2))) * k * e / r
+        assert np.allclose(out, ref, rtol=1e-13, atol=0), pbc
