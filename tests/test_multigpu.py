@@ -107,6 +107,34 @@ def test_balanced_partition(kmc):
     assert c.sum() == 100 and (c >= 0).all()
 
 
+def test_brick_order_gives_slab_partitions_with_thin_halos(kmc, orc):
+    """With the bandwidth-minimised 'brick' order (cubes ordered y-major) contiguous row blocks are lateral slabs: in a
+    4-rank split every rank exchanges halo rows with its 1-2 slab neighbours only and sends a small fraction of its rows,
+    whereas the tile-by-tile 'file' order makes every rank talk to every other rank."""
+    mg = importlib.import_module(PKG + ".multigpu")
+    syn = importlib.import_module(PKG + ".synthetic")
+    P = 4
+    stats = {}
+    for order in ("brick", "file"):
+        s = syn.crossbar_standin(os.path.join(ROOT, "tests", "golden", "5nm_device", "parameters.txt"), 2, 2, order=order,
+                                 vacancy_concentration=0.0)
+        sp = orc.sparsity_K(s.x, s.y, s.z, s.lattice, s.pbc, s.nn_dist, s.N_left, s.N_right, use_cells=True)
+        rp, col = sp["row_ptr"], sp["col"]
+        n = len(rp) - 1
+        counts, displs = mg.balanced_partition(np.diff(rp), P)
+        need = np.stack([mg.need_map_numpy(rp[displs[r]:displs[r] + counts[r] + 1] - rp[displs[r]],
+                                           col[rp[displs[r]]:rp[displs[r] + counts[r]]], int(displs[r]), int(counts[r]), n)
+                         for r in range(P)])
+        peers = [bin(mg.recv_mask_numpy(need[r], r, counts, displs)).count("1") for r in range(P)]
+        sent = [int((mg.send_masks_numpy(need, r, counts, displs) != 0).sum()) / max(int(counts[r]), 1) for r in range(P)]
+        stats[order] = (peers, sent)
+    peers_b, sent_b = stats["brick"]
+    peers_f, sent_f = stats["file"]
+    assert max(peers_b) <= 2 and peers_b[0] == 1 and peers_b[-1] == 1, stats
+    assert max(sent_b) < 0.25, stats
+    assert max(peers_f) == P - 1 and max(sent_f) > max(sent_b), stats
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("which", ["5nm", "file"])
 def test_sharded_solve_bit_identical_to_single_gpu(which):
