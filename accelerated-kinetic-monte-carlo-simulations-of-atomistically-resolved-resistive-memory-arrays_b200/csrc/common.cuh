@@ -64,6 +64,8 @@ struct kmcb200_ctx {
     // dot/pcg workspace
     CgState *cg_state = nullptr;  // device
     bool cg_done_stale = false;   // a PCG solve ended abnormally: CgState::done may still be set
+    // opted-in dynamic shared memory per kernel family (function attributes are per device, a ctx is bound to one)
+    size_t smem_cfg_events = 0, smem_cfg_coulomb = 48 * 1024, smem_cfg_staged = 0;
     double *partials = nullptr;   // device, 2 * max chunks
     size_t partials_cap = 0;
 };

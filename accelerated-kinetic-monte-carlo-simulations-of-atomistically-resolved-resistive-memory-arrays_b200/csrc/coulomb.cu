@@ -408,10 +408,9 @@ extern "C" int kmcb200_poisson_gridless(kmcb200_ctx *ctx, int N, const double *x
             kmc_set_error("Coulomb sum: %d charged sources around one 20 A cell exceed the shared-memory sort capacity", max_nbr);
             return KMCB200_E_CAPACITY;
         }
-        static size_t configured = 48 * 1024;
-        if (dyn > configured) {
+        if (dyn > ctx->smem_cfg_coulomb) {
             KMC_CUDA(cudaFuncSetAttribute(nbr_fill_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-            configured = dyn;
+            ctx->smem_cfg_coulomb = dyn;
         }
         kmc_count_launch();
         nbr_fill_sort_kernel<<<P.ncell, 128, dyn, ctx->stream>>>(P.g.nx, P.g.ny, P.g.nz, P.src_cstart, src_by_cell, P.list_start,

@@ -888,10 +888,9 @@ extern "C" int kmcb200_execute_kmc_step(kmcb200_ctx *ctx, kmcb200_events *ev, in
     size_t dyn = (size_t)(2 * ev->nsuper * 256) * sizeof(double);
     a.chunks_in_smem = dyn <= 190 * 1024 ? 1 : 0;
     if (getenv("KMCB200_EV_NO_SMEM")) a.chunks_in_smem = 0;  // tests: exercise the large-device (> 3.2 M sites) path
-    static bool configured = false;
-    if (a.chunks_in_smem && !configured) {
+    if (a.chunks_in_smem && ctx->smem_cfg_events == 0) {
         KMC_CUDA(cudaFuncSetAttribute(event_loop_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(190 * 1024)));
-        configured = true;
+        ctx->smem_cfg_events = 190 * 1024;
     }
     kmc_count_launch();
     if (a.chunks_in_smem) event_loop_kernel<true><<<1, EV_THREADS, dyn, ctx->stream>>>(a);

@@ -438,11 +438,10 @@ static int spmv_launch(kmcb200_ctx *ctx, kmcb200_kmat *K, const double *xg, doub
     // The staged kernel only pays off when the rows of a chunk share columns (reuse >> 1); for the DeviceKMC lattices
     // the measured reuse is 1.3-1.7 and it is SLOWER (371 us vs 197 us at 62 M nnz), so it is opt-in.
     if (K->plan_max_unique > 0 && dyn <= 200 * 1024 && cm.size == 1) {
-        static size_t configured = 0;
-        if (dyn > configured) {
+        if (dyn > ctx->smem_cfg_staged) {
             KMC_CUDA(cudaFuncSetAttribute(spmv_staged_kernel<L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
             KMC_CUDA(cudaFuncSetAttribute(spmv_staged_kernel<L, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-            configured = dyn;
+            ctx->smem_cfg_staged = dyn;
         }
         if (with_dot)
             spmv_staged_kernel<L, true><<<blocks, CH, dyn, ctx->stream>>>(K->rows, K->row_ptr, K->lcol, K->val, K->u_ptr,
