@@ -12,6 +12,10 @@
  *
  * All work is enqueued on the context's stream; calls return without a host synchronisation unless
  * they hand a host scalar back (documented per function).
+ *
+ * Process model: one process per GPU, as the reference runs one MPI rank per GCD.  A context is bound to
+ * the device given to kmcb200_create(), which also makes that device current; calls on a context must be
+ * made with its device current and from one host thread at a time.
  */
 #ifndef KMC_B200_H
 #define KMC_B200_H
