@@ -76,6 +76,12 @@ def build_workload(kmc, name):
         return kmc.load_structure(PARAM_5NM), "structures/5nm_device (shipped), N=37650"
     base, _, order = name.partition("_")
     order = order or "file"
+    if base == "highvac7x7":
+        # BASELINE.json config 5: ~2 M sites, 25 % of the oxygen sites are vacancies (stresses the charge sum and the
+        # rate list / event selection), Vd = 5
+        s = syn.crossbar_standin(PARAM_5NM, 7, 7, order=order, Vd=5.0, rnd_seed=5, vacancy_concentration=0.25)
+        return s, (f"synthetic high-vacancy lattice: 7x7 lateral tiling of the shipped 5nm cell, N={s.N}, 25 % oxygen "
+                   f"vacancies, Vd=5, site order '{order}'")
     t = {"standin8x8": 8, "standin4x4": 4, "standin2x2": 2, "standin16x16": 16}[base]
     s = syn.crossbar_standin(PARAM_5NM, t, t, order=order, Vd=15.0, rnd_seed=32)
     note = {"file": "site order 'file' (tile images site-major: the 5nm file's block structure, wide K bandwidth)",
