@@ -172,12 +172,12 @@ def pcg_jacobi(row_ptr, col, data, inv_diag, rhs, x0, tol, max_it=10000, lanes=8
     return x, r, it, stats
 
 
-def coulomb(x, y, z, element, charge, sigma, k, cutoff=20.0, row_start=0, row_count=None):
+def coulomb(x, y, z, element, charge, sigma, k, cutoff=20.0, row_start=0, row_count=None, use_cells=False):
     x, y, z, element, charge = _d(x), _d(y), _d(z), _i(element), _i(charge)
     N = len(x)
     row_count = N - row_start if row_count is None else row_count
     pot = np.zeros(N)
-    lib().orc_coulomb(C.c_int(N), _p(x), _p(y), _p(z), _p(element), _p(charge), C.c_double(sigma), C.c_double(k),
+    (lib().orc_coulomb_cells if use_cells else lib().orc_coulomb)(C.c_int(N), _p(x), _p(y), _p(z), _p(element), _p(charge), C.c_double(sigma), C.c_double(k),
                       C.c_double(cutoff), C.c_int(row_start), C.c_int(row_count), _p(pot))
     return pot
 

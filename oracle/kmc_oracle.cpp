@@ -627,6 +627,68 @@ void orc_coulomb(int N, const double *x, const double *y, const double *z, const
     }
 }
 
+// a8 with a 20 A cell grid as the candidate enumerator (same predicate, same ascending-j summation order as
+// orc_coulomb, hence bit-identical results; tests/test_oracle.py checks that).  This is the variant orc_superstep and the
+// CPU baseline use: the all-sources loop above is O(N*Q).
+void orc_coulomb_cells(int N, const double *x, const double *y, const double *z, const int *element,
+                       const int *charge, double sigma, double k, double cutoff, int row_start, int row_count,
+                       double *pot) {
+    std::vector<int> q;  // ascending j
+    for (int j = 0; j < N; ++j)
+        if (charge[j] != 0 && possibly_charged(element[j])) q.push_back(j);
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int i = 0; i < N; ++i) {
+        lo[0] = std::min(lo[0], x[i]); hi[0] = std::max(hi[0], x[i]);
+        lo[1] = std::min(lo[1], y[i]); hi[1] = std::max(hi[1], y[i]);
+        lo[2] = std::min(lo[2], z[i]); hi[2] = std::max(hi[2], z[i]);
+    }
+    if (N == 0) return;
+    const double h = cutoff * 1.0001;
+    int nc[3];
+    for (int d = 0; d < 3; ++d) nc[d] = std::max(1, (int)std::floor((hi[d] - lo[d]) / h) + 1);
+    auto cidx = [&](double v, int d) { int c = (int)std::floor((v - lo[d]) / h); return std::min(std::max(c, 0), nc[d] - 1); };
+    size_t ncell = (size_t)nc[0] * nc[1] * nc[2];
+    std::vector<int> start(ncell + 1, 0), items(q.size());
+    std::vector<int> cid(q.size());
+    for (size_t s = 0; s < q.size(); ++s) {
+        int j = q[s];
+        cid[s] = (cidx(x[j], 0) * nc[1] + cidx(y[j], 1)) * nc[2] + cidx(z[j], 2);
+        start[cid[s] + 1]++;
+    }
+    for (size_t c = 0; c < ncell; ++c) start[c + 1] += start[c];
+    {
+        std::vector<int> fill(start.begin(), start.end() - 1);
+        for (size_t s = 0; s < q.size(); ++s) items[fill[cid[s]]++] = q[s];  // ascending j inside a cell
+    }
+#pragma omp parallel
+    {
+        std::vector<int> cand;
+#pragma omp for schedule(dynamic, 256)
+        for (int idx = 0; idx < row_count; ++idx) {
+            int i = idx + row_start;
+            cand.clear();
+            int a = cidx(x[i], 0), b = cidx(y[i], 1), c = cidx(z[i], 2);
+            for (int da = -1; da <= 1; ++da) for (int db = -1; db <= 1; ++db) for (int dc = -1; dc <= 1; ++dc) {
+                int aa = a + da, bb = b + db, cc = c + dc;
+                if (aa < 0 || aa >= nc[0] || bb < 0 || bb >= nc[1] || cc < 0 || cc >= nc[2]) continue;
+                size_t cell = ((size_t)aa * nc[1] + bb) * nc[2] + cc;
+                for (int s = start[cell]; s < start[cell + 1]; ++s) cand.push_back(items[s]);
+            }
+            std::sort(cand.begin(), cand.end());
+            double local = 0.0;
+            for (int j : cand) {
+                if (i == j) continue;
+                double d = dist_nopbc(x[i], y[i], z[i], x[j], y[j], z[j]);
+                if (d < cutoff) {
+                    double dist = 1e-10 * d;
+                    local += v_solve(dist, charge[j], sigma, k);
+                }
+            }
+            pot[i] = local;
+        }
+    }
+}
+
 // a10: kmc_events.cu:130-229
 void orc_build_events(int N, int nn, const int *neigh, const int *layer, double T_bg, double freq, double sigma,
                       double k, const double *x, const double *y, const double *z, const double *pot,
@@ -803,7 +865,7 @@ void orc_superstep(const orc_params *p, const double *x, const double *y, const 
     info->cg_iterations = orc_pcg_jacobi(n, row_ptr, col, data.data(), inv_diag.data(), rhs.data(),
                                          pot_boundary + NL, tol, p->cg_max_it, p->spmv_lanes, nullptr);
     double t2 = now_s();
-    orc_coulomb(N, x, y, z, element, charge, p->sigma, p->k, p->cutoff_radius, 0, N, pot_total);
+    orc_coulomb_cells(N, x, y, z, element, charge, p->sigma, p->k, p->cutoff_radius, 0, N, pot_total);
     double t3 = now_s();
     for (int i = 0; i < N; ++i) pot_total[i] += pot_boundary[i];  // potential_solver_gpu.cu:832-843,1147
     std::vector<int> type((size_t)N * nn);

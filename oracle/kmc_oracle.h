@@ -98,6 +98,11 @@ void orc_coulomb(int N, const double *x, const double *y, const double *z, const
                  const int *charge, double sigma, double k, double cutoff, int row_start,
                  int row_count, double *pot_out /* indexed by global site id */);
 
+/* same result bit for bit, candidates enumerated through a 20 A cell grid instead of the all-sources loop */
+void orc_coulomb_cells(int N, const double *x, const double *y, const double *z, const int *element,
+                       const int *charge, double sigma, double k, double cutoff, int row_start,
+                       int row_count, double *pot_out);
+
 /* ---- a10: event rates (kmc_events.cu:130-229) ----------------------------------- */
 void orc_build_events(int N, int nn, const int *neigh, const int *layer, double T_bg, double freq,
                       double sigma, double k, const double *x, const double *y, const double *z,

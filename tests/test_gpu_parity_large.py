@@ -1,0 +1,93 @@
+"""GPU parity on the kernel instantiations bench.py actually runs.
+
+The 5 nm device (143 dot chunks, 1 event super) only reaches the FUSE=true PCG kernels and the single-super event
+hierarchy.  The lattices here are large enough for
+  * nchunks > 1024  -> spmv_kernel<..,FUSE=false> + dot_finalize_kernel + cg_update_kernel<false> + cg_init_kernel<false>
+  * nsuper  > 1     -> the top-level scan over several supers, super_list / super_flag repair, cross-super prefix
+                       subtraction in the selector (reference semantics: kmc_events.cu:448-516, upper_bound on the scan)
+and are still small enough for the CPU oracle (seconds per superstep).  Every comparison is against the ORACLE.
+Bit-exact: CSR sparsity, PCG iteration count, boundary potential (no transcendental functions), event log, elements,
+charges.  Total potential / event time: 1e-10 relative (erfc / exp / log ulps), as north_star states.
+"""
+import importlib
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLD, PKG
+
+pytestmark = pytest.mark.gpu
+PARAM_5NM = os.path.join(GOLD, "5nm_device", "parameters.txt")
+
+
+def to_np(t):
+    return t.detach().cpu().numpy()
+
+
+def _standin(kmc, t, **kw):
+    syn = importlib.import_module(PKG + ".synthetic")
+    return syn.crossbar_standin(PARAM_5NM, t, t, order="brick", **kw)
+
+
+def _check_supersteps(kmc, ctx, orc, s, nsteps, expect_types=None):
+    dev = kmc.DeviceKMC(s, ctx=ctx)
+    sim = orc.OracleSim(s, use_cells=True)
+    K = dev.K.to_host()
+    for k in ("row_ptr", "col", "left_row_ptr", "left_col", "right_row_ptr", "right_col"):
+        assert (K[k] == sim.sp[k]).all(), k
+    nchunks = (dev.K.rows + 255) // 256
+    nsuper = ((s.N + 255) // 256 + 255) // 256
+    assert nchunks > 1024, "this test must reach the FUSE=false PCG kernels (what bench.py runs)"
+    assert nsuper > 1, "this test must reach the multi-super event hierarchy (what bench.py runs)"
+    seen = np.zeros(5, dtype=np.int64)
+    for step in range(nsteps):
+        et, ne = dev.superstep()
+        log, psum = dev.ev.log()
+        r = sim.superstep(max_log=1 << 16)
+        assert dev.last_cg_iterations == r["cg_iterations"], (step, dev.last_cg_iterations, r["cg_iterations"])
+        assert r["cg_iterations"] > 0
+        assert (to_np(dev.pot_boundary) == sim.pot_boundary).all(), f"step {step}: boundary potential not bit-identical"
+        assert ne == r["n_events"], (step, ne, r["n_events"])
+        ev = r["events"]
+        bad = np.nonzero((log != ev).any(axis=1))[0]
+        assert bad.size == 0, f"step {step}: first divergent event {bad[0]}: gpu {log[bad[0]]} oracle {ev[bad[0]]}"
+        assert (to_np(dev.element) == sim.element).all() and (to_np(dev.charge) == sim.charge).all()
+        pot = to_np(dev.pot_charge)
+        assert np.abs(pot - sim.pot_total).max() <= 1e-10 * np.abs(sim.pot_total).max()
+        assert abs(et - r["event_time"]) <= 1e-10 * r["event_time"]
+        seen += np.bincount(ev[:, 2], minlength=5)
+        # events landed in more than one super: the cross-super selection path was exercised
+        assert len(np.unique(ev[:, 0] >> 16)) > 1
+    if expect_types is not None:
+        assert (seen[:4] > 0).sum() >= expect_types, seen
+    mt, pos = dev.ev.rng_get_state()
+    omt, opos = sim.rng.state()
+    assert pos == opos and (mt == omt).all()
+    dev.ev.close(); dev.K.close()
+    return seen
+
+
+@pytest.mark.parametrize("no_smem", [False, True])
+def test_standin4x4_brick_two_supersteps_vs_oracle(kmc, ctx, orc, no_smem):
+    """4x4 'brick' stand-in (602 400 sites, 2 282 dot chunks, 10 supers): cold + warm superstep, once with
+    event_loop_kernel<true> (chunk sums in shared memory) and once with event_loop_kernel<false> (KMCB200_EV_NO_SMEM)."""
+    s = _standin(kmc, 4, Vd=15.0, rnd_seed=32)
+    assert s.N == 602400
+    old = os.environ.pop("KMCB200_EV_NO_SMEM", None)
+    try:
+        if no_smem:
+            os.environ["KMCB200_EV_NO_SMEM"] = "1"
+        _check_supersteps(kmc, ctx, orc, s, 2)
+    finally:
+        os.environ.pop("KMCB200_EV_NO_SMEM", None)
+        if old is not None:
+            os.environ["KMCB200_EV_NO_SMEM"] = old
+
+
+def test_highvac3x3_brick_superstep_vs_oracle(kmc, ctx, orc):
+    """BASELINE config 5 at 3x3 (338 850 sites, 25 % oxygen vacancies, Vd = 5): thousands of PCG iterations on the
+    badly conditioned vacancy-rich K, ~1e4 charged sources in the Coulomb sum, all four event classes active."""
+    s = _standin(kmc, 3, Vd=5.0, rnd_seed=5, vacancy_concentration=0.25)
+    seen = _check_supersteps(kmc, ctx, orc, s, 1, expect_types=3)
+    assert seen[kmc.VACANCY_GENERATION] > 0 and seen[kmc.VACANCY_RECOMBINATION] > 0

@@ -85,6 +85,17 @@ def test_cutoff_list_equivalent_to_inline_predicate(kmc, orc, s_small):
         assert abs(acc - pot[i]) <= 1e-13 * max(1e-30, abs(acc))
 
 
+def test_coulomb_cell_variant_is_bit_identical(kmc, orc, s_small, s5):
+    """orc_coulomb_cells (what orc_superstep / the CPU baseline run) == the all-sources loop, bit for bit"""
+    for s, cut in ((s_small, 6.0), (s_small, 20.0), (s5, 20.0)):
+        charge = np.zeros(s.N, np.int32); charge[s.element == kmc.VACANCY] = 2; charge[s.element == kmc.OXYGEN_DEFECT] = -2
+        a = orc.coulomb(s.x, s.y, s.z, s.element, charge, s.sigma, s.k, cutoff=cut)
+        b = orc.coulomb(s.x, s.y, s.z, s.element, charge, s.sigma, s.k, cutoff=cut, use_cells=True)
+        assert (a == b).all() and np.abs(a).max() > 0
+    part = orc.coulomb(s5.x, s5.y, s5.z, s5.element, charge, s5.sigma, s5.k, row_start=9000, row_count=500, use_cells=True)
+    assert (part[9000:9500] == a[9000:9500]).all() and (part[:9000] == 0).all()
+
+
 def test_summation_spec(orc):
     rng = np.random.default_rng(0)
     for n in (1, 100, 256, 257, 5000):
