@@ -18,7 +18,6 @@
 
 namespace {
 constexpr int EV_THREADS = 512;
-constexpr int MAX_DIRTY = 1024;
 constexpr int MAX_SUPER = 256;
 }  // namespace
 
@@ -30,7 +29,7 @@ struct EvResult {
     double event_time;
     double psum_last;
     int n_events;
-    int error;  // 1: dirty list overflow
+    int error;  // reserved (always 0: the per-event work lists are bounded by 2 * REV_STRIDE + 2 chunks)
 };
 
 struct kmcb200_events {
@@ -42,7 +41,10 @@ struct kmcb200_events {
     double *rowsum = nullptr, *chunksum = nullptr, *supersum = nullptr;
     // inclusive scan_256 prefixes kept next to the sums, so the selector compares instead of re-scanning:
     // rowincl[256 c + t] over the rows of chunk c, chunkincl[256 s + t] over the chunks of super s (both padded)
+    // (rowsum and rowincl share ONE allocation: rowincl = rowsum + nchunk*256, so a single L2 access-policy window covers both)
     double *rowincl = nullptr, *chunkincl = nullptr;
+    size_t l2_window_bytes = 0;  // 0: no persisting-L2 window (not supported / disabled)
+    float l2_hit_ratio = 1.0f;
     int *rev = nullptr;  // N * REV_STRIDE
     unsigned *mt = nullptr;  // 624 words + pos
     int *log = nullptr;
@@ -135,7 +137,7 @@ __device__ __forceinline__ int warp_pick_256(const Scan256 &sc, const double v[8
 // The same selection from STORED inclusive prefixes (inc = incl[8 lane .. 8 lane + 7]); the values themselves are only
 // needed when no prefix exceeds number (load_v fetches them then).
 template <class LoadV>
-__device__ __forceinline__ int warp_pick_incl(const double inc[8], double number, double *prev, LoadV load_v) {
+__device__ __forceinline__ int warp_pick_incl(const double inc[8], double number, double *prev, double *cur, LoadV load_v) {
     int kfirst = 8;
 #pragma unroll
     for (int k = 7; k >= 0; --k)
@@ -158,16 +160,22 @@ __device__ __forceinline__ int warp_pick_incl(const double inc[8], double number
             tsel = l * 8 + __shfl_sync(KMC_FULL_MASK, klast, l);
         }
     }
-    double pv = 0.0;
-    if (tsel > 0) {
-        int pl = (tsel - 1) >> 3, pk = (tsel - 1) & 7;
-        double cand = inc[0];
+    double pv = 0.0, cv = 0.0;
+    if (tsel >= 0) {  // prev = incl[tsel - 1] (0 for tsel == 0), cur = incl[tsel]
+        const int pt = tsel > 0 ? tsel - 1 : 0;
+        const int pl = pt >> 3, pk = pt & 7, cl = tsel >> 3, ck = tsel & 7;
+        double candp = inc[0], candc = inc[0];
 #pragma unroll
-        for (int k = 1; k < 8; ++k)
-            if (k == pk) cand = inc[k];
-        pv = __shfl_sync(KMC_FULL_MASK, cand, pl);
+        for (int k = 1; k < 8; ++k) {
+            if (k == pk) candp = inc[k];
+            if (k == ck) candc = inc[k];
+        }
+        pv = __shfl_sync(KMC_FULL_MASK, candp, pl);
+        cv = __shfl_sync(KMC_FULL_MASK, candc, cl);
+        if (tsel == 0) pv = 0.0;
     }
     *prev = pv;
+    *cur = cv;
     return tsel;
 }
 // butterfly row sum of the summation spec: lane l holds p[l] + p[l+32]
@@ -330,8 +338,13 @@ __device__ __forceinline__ double mt_next_double(unsigned *mt, int &pos) {
 
 #ifdef KMC_EV_PROFILE
 #define EV_TICK(k) do { if (tid == 0) { long long now_ = clock64(); ph[k] += now_ - t_last; t_last = now_; } } while (0)
+// finer, per warp: W_START() sets the warp's reference time, W_TICK(k) adds the time since the last tick to counter k
+#define W_START() do { wt_last = clock64(); } while (0)
+#define W_TICK(k) do { __syncwarp(); long long now_ = clock64(); if (lane == 0) atomicAdd(&s_prof[k], (unsigned long long)(now_ - wt_last)); wt_last = now_; } while (0)
 #else
 #define EV_TICK(k) do { } while (0)
+#define W_START() do { } while (0)
+#define W_TICK(k) do { } while (0)
 #endif
 
 struct EvLoopArgs {
@@ -350,151 +363,202 @@ struct EvLoopArgs {
     double *log_psum;
     int log_cap;
     EvResult *result;
-    int chunks_in_smem;  // chunk sums cached in dynamic shared memory for the whole loop
+    int use_spec;  // warp 15 predicts the next event and stages its data in shared memory (never changes a result)
     long long *phase_cycles;  // 16 counters (KMC_EV_PROFILE builds)
 };
 
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-__device__ __forceinline__ bool smem_set_insert(int *table, int mask, int key) {
-    // open addressing; returns true if key was not present.  table entries are -1 when empty.
-    unsigned h = ((unsigned)key * 2654435761u) >> 7;
-    for (int probe = 0; probe <= mask; ++probe) {
-        int slot = (int)((h + probe) & (unsigned)mask);
-        int old = atomicCAS(table + slot, -1, key);
-        if (old == -1) return true;
-        if (old == key) return false;
+// Shared-memory layout of a 256-group that one warp scans (lane l owns elements 8l..8l+7): element t lives at
+// (t & 7) * 32 + (t >> 3), so the 32 lanes of a warp reading "their k-th element" hit 32 consecutive doubles (no bank
+// conflicts; the natural layout is a 16-way conflict on every one of the 8 loads).
+__device__ __forceinline__ int tpos(int t) { return ((t & 7) << 5) | (t >> 3); }
+
+// Device-resident MT19937 that may run ahead of what the loop consumes (the uniforms of event e+2 are drawn while event
+// e is repaired).  block_start = number of 32-bit words produced before the current 624-word block began; the state
+// before the latest twist is kept, so at loop exit the generator can be handed back exactly `consumed` words in -- in
+// step with the host generator of the reference (src/kmc_events.cu:469,515: two doubles per event).
+struct EvRng {
+    unsigned mt[624], backup[624];
+    int pos;
+    long long block_start, prev_block_start;
+};
+__device__ __forceinline__ unsigned evrng_next32(EvRng &g) {
+    if (g.pos >= 624) {
+        for (int q = 0; q < 624; ++q) g.backup[q] = g.mt[q];
+        g.prev_block_start = g.block_start;
+        g.block_start += 624;
     }
-    return true;  // table full: treat as new (duplicates only cost redundant work)
+    return mt_next32(g.mt, g.pos);
+}
+__device__ __forceinline__ double evrng_next_double(EvRng &g) {
+    double x0 = (double)evrng_next32(g);
+    double x1 = (double)evrng_next32(g);
+    double sum = x0 + x1 * 4294967296.0;
+    double ret = sum / 18446744073709551616.0;
+    if (ret >= 1.0) ret = 0.99999999999999988897769753748;  // nextafter(1.0, 0.0)
+    return ret;
 }
 
-// Draws the (u1, u2) pair of one event ahead of time.  Remembers how to undo it (position + pre-twist state), because
-// the pair drawn for the event that ends the loop is never consumed and the generator must stay in step with the host's.
-__device__ __forceinline__ void rng_prefetch_pair(unsigned *mt, unsigned *mt_backup, int *mtpos, int *pos_before,
-                                                  int *backup_valid, double *pair) {
-    int pos = *mtpos;
-    *pos_before = pos;
-    if (pos + 4 > 624) {
-        for (int q = 0; q < 624; ++q) mt_backup[q] = mt[q];
-        *backup_valid = 1;
-    } else {
-        *backup_valid = 0;
-    }
-    pair[0] = mt_next_double(mt, pos);
-    pair[1] = mt_next_double(mt, pos);
-    *mtpos = pos;
-}
+// One event record, double buffered by event parity: the selector of event e+1 may run while event e is still applied
+// to element/charge and logged.
+struct EvRecord {
+    int i, j, ty, slot;
+    double psum;
+    double pos, w;  // cumulative rate in front of row i and the row's total rate (for the predictor, approximate)
+};
 
-// The persistent event loop: ONE CTA.  Every phase issues all its global loads together, so a phase costs about
-// one L2/DRAM round trip; 5 block barriers per event:
-//   S   warp 0 (selector, warp-synchronous): top level = scan_256 of the super sums; chunk and row level = compare
-//       against the STORED inclusive prefixes (chunkincl in shared memory, rowincl: 1 RT); slot level = ordered walk
-//       over the row's non-zero slots (1 RT); publishes (i, j, type); prefetches the reverse-index rows of i and of
-//       every candidate j into L2.  Warp 1 meanwhile draws the uniforms of the NEXT event.
-//   Z   all warps: zero-out through the fixed-stride reverse index (1 RT + 1 RT) + list of touched rows / unique
-//       chunks / supers; one spare thread applies the event to element/charge, another draws the residence time
-//   R1  one warp per touched row: butterfly row sum (1 RT)
-//   R2  one warp per touched chunk: scan_256 of its 256 row sums (1 RT) -> chunk sum + the chunk's stored prefixes
-//   U   one warp per touched super: scan_256 of its chunk sums (shared memory) -> super sum + stored prefixes
-// Measured budget and the building-block latencies: DESIGN.md section 3 ("Events").
-// SMEM: chunk sums + their stored prefixes live in dynamic shared memory (both padded to whole supers with zeros).
+// The persistent event loop: ONE CTA of 16 warps, three block barriers per event.
+//   S   one warp (elected, see R2): top level = scan_256 of the super sums; chunk and row level = compare against the
+//       STORED inclusive prefixes (chunk level in shared memory, row level from global memory); slot level = ordered walk
+//       over the row's non-zero slots; publishes (i, j, type) and the residence time.  The two global round trips of this
+//       phase (the chunk's 256 row prefixes, the row's rates / neighbours / types) are normally served from shared memory:
+//       see P.
+//   ---- barrier A
+//   Z   4 warps: zero-out through the fixed-stride reverse index (2 dependent round trips) + list of rows that lost a rate
+//   ---- barrier B1
+//   R1  one warp per such row: butterfly row sum, dirty-chunk bitmap + list
+//   ---- barrier B2
+//   R2  one warp per dirty chunk: scan_256 of its 256 row sums -> chunk sum + stored row prefixes.  The warp that
+//       finishes the LAST dirty chunk of a super re-scans that super; the warp that finishes the LAST dirty super is the
+//       selector of the next event and goes straight on to S (counters in shared memory instead of two more barriers).
+//   H   warp 14, during R: applies the event to element/charge, writes the log, draws the uniforms of the event after next.
+//   P   warp 15, from barrier A on: PREDICTS the next event's chunk and row from the not-yet-repaired sums (corrected for
+//       the rate the current event removes) and copies that chunk's row prefixes and that row's slots into shared memory
+//       while Z / R1 / R2 run.  The selector repeats the exact selection on the repaired sums and uses the copies only if
+//       it arrives at the same chunk / row and no row of that chunk changed in between -- the copies are then bit-identical
+//       to what it would load, so speculation never changes a result, it only hides two memory round trips.
+// SMEM: chunk sums + their stored prefixes live in dynamic shared memory (padded to whole supers with zeros).
 template <bool SMEM>
 __global__ void __launch_bounds__(EV_THREADS, 1) event_loop_kernel(EvLoopArgs a) {
-    extern __shared__ double cs_smem[];  // [nsuper*256] chunk sums, then [nsuper*256] inclusive prefixes
-    __shared__ unsigned mt[624];
-    __shared__ double ss[MAX_SUPER];
-    __shared__ int rows_list[MAX_DIRTY], chunk_list[MAX_DIRTY], super_list[MAX_SUPER];
-    __shared__ int chunk_set[1024];
-    __shared__ int super_flag[MAX_SUPER];
+    extern __shared__ double cs_smem[];  // [nsuper*256] chunk sums, then [nsuper*256] inclusive prefixes (tpos layout)
+    __shared__ EvRng rng;
+    __shared__ double ss[MAX_SUPER];           // super sums, tpos layout
+    __shared__ double s_u1[4], s_lg[4];         // per event (ring of 4): selection uniform, -log(time uniform)
+    __shared__ EvRecord s_rec[2];
+    __shared__ unsigned chunk_bits[2048];       // dirty bitmap over <= 65536 chunks
+    __shared__ int rows_list[2 * REV_STRIDE];
+    __shared__ int chunk_list[2 * REV_STRIDE + 2];
+    __shared__ int super_cnt[MAX_SUPER];        // dirty chunks of a super still to be re-scanned
     __shared__ int n_rows, n_chunks, n_supers;
-    __shared__ double s_event_time, s_u2, s_psum;
-    __shared__ double s_upair[2][2];  // uniforms of event e live in s_upair[e & 1] (drawn one event ahead by warp 1)
-    __shared__ unsigned mt_backup[624];
-    __shared__ int s_pos_before, s_backup_valid;
-    __shared__ int s_i, s_j, s_ty, s_slot, s_stop, s_nevents, s_error, s_mtpos;
+    __shared__ double s_event_time;
+    __shared__ int s_stop, s_nevents;
+    // predictor -> selector
+    __shared__ double s_spec_incl[256];         // row prefixes of the predicted chunk, tpos layout
+    __shared__ double s_spec_p[64];             // rates of the predicted row
+    __shared__ int s_spec_nb[64], s_spec_ty[64];
+    __shared__ int s_spec_chunk, s_spec_r, s_spec_valid;
+    __shared__ int s_spec_ready;                // = e once the speculation for event e is complete
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     constexpr int NW = EV_THREADS / 32;
+    constexpr int PW = NW - 1, HW = NW - 2;  // predictor / housekeeping warps
+    constexpr int NCW = NW - 2;              // warps that take row / chunk work in R1 / R2
     const int nn = a.nn;
 #ifdef KMC_EV_PROFILE
     long long ph[16] = {0};
     long long t_last = clock64();
+    long long wt_last = 0;
+    __shared__ unsigned long long s_prof[16];
+    if (tid < 16) s_prof[tid] = 0;
 #endif
     const int npad = (int)a.nsuper * 256;  // chunk arrays are padded to whole supers (tail = 0)
     double *cs, *ci;                       // chunk sums / inclusive prefixes of the chunk sums per super
     if (SMEM) {
         cs = cs_smem;
         ci = cs_smem + npad;
-        for (int q = tid; q < npad; q += EV_THREADS) { cs[q] = a.chunksum[q]; ci[q] = a.chunkincl[q]; }
+        for (int q = tid; q < npad; q += EV_THREADS) {
+            const int d = (q & ~255) | tpos(q & 255);
+            cs[d] = a.chunksum[q];
+            ci[d] = a.chunkincl[q];
+        }
     } else {
         cs = a.chunksum;
         ci = a.chunkincl;
     }
-    for (int q = tid; q < 624; q += EV_THREADS) mt[q] = a.mt_state[q];
+    // element t (0..255) of super s inside cs / ci
+#define KMC_CS(s_, k_) (SMEM ? ((s_) * 256 + 32 * (k_) + lane) : ((s_) * 256 + 8 * lane + (k_)))
+#define KMC_CIDX(c) (SMEM ? (((c) & ~255) | tpos((c) & 255)) : (c))
+    for (int q = tid; q < 624; q += EV_THREADS) rng.mt[q] = a.mt_state[q];
     for (int q = tid; q < MAX_SUPER; q += EV_THREADS) {
-        ss[q] = (q < a.nsuper) ? a.supersum[q] : 0.0;
-        super_flag[q] = 0;
+        ss[tpos(q)] = (q < a.nsuper) ? a.supersum[q] : 0.0;
+        super_cnt[q] = 0;
     }
-    for (int q = tid; q < 1024; q += EV_THREADS) chunk_set[q] = -1;
+    for (int q = tid; q < 2048; q += EV_THREADS) chunk_bits[q] = 0u;
     if (tid == 0) {
-        s_mtpos = (int)a.mt_state[624];
+        rng.pos = (int)a.mt_state[624];
+        rng.block_start = -(long long)rng.pos;
+        rng.prev_block_start = rng.block_start;
         s_event_time = 0.0;
         s_nevents = 0;
-        s_error = 0;
         s_stop = 0;
-        n_rows = 0; n_chunks = 0; n_supers = 0;
+        n_rows = 0;
+        n_chunks = 0;
+        n_supers = 0;
+        s_spec_chunk = -1; s_spec_r = -1; s_spec_valid = 0; s_spec_ready = 0;
     }
     __syncthreads();
-    if (tid == 32) rng_prefetch_pair(mt, mt_backup, &s_mtpos, &s_pos_before, &s_backup_valid, s_upair[0]);
+    if (tid == 0) {
+        for (int e = 0; e < 2; ++e) {  // uniforms of events 0 and 1
+            s_u1[e] = evrng_next_double(rng);
+            s_lg[e] = -log(evrng_next_double(rng));
+        }
+    }
     __syncthreads();
 
+    bool i_select = (warp == 0);
     while (true) {
-        // =============================== S: selector, warp 0 ===========================================
-        if (warp == 1 && lane == 0) {  // draw the uniforms of the NEXT event while warp 0 selects the current one
-            bool go1 = (s_event_time < a.inv_freq_threshold) && (a.max_events <= 0 || s_nevents < a.max_events) && !s_error;
-            if (go1) rng_prefetch_pair(mt, mt_backup, &s_mtpos, &s_pos_before, &s_backup_valid, s_upair[(s_nevents + 1) & 1]);
-        }
-        if (warp == 0) {
-            bool go = (s_event_time < a.inv_freq_threshold) && (a.max_events <= 0 || s_nevents < a.max_events) && !s_error;
+        // =============================== S: selector (one warp, warp-synchronous) =============================
+        if (i_select) {
+            const int e = s_nevents;  // index of the event selected now
+            const bool go = (s_event_time < a.inv_freq_threshold) && (a.max_events <= 0 || e < a.max_events);
             int ei = -1, ej = -1, ety = KMCB200_NULL_EVENT, eslot = -1;
+            double Psum = 0.0, pos = 0.0, wrow = 0.0;
+            W_START();
             if (go) {
                 // ---- top level: scan_256 over the super sums (shared memory) ------------------------------
                 Scan256 sc;
                 double v[8];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) { v[k] = ss[8 * lane + k]; sc.a[k] = v[k]; }
+                for (int k = 0; k < 8; ++k) { v[k] = ss[32 * k + lane]; sc.a[k] = v[k]; }
                 warp_scan_256(sc);
-                const double Psum = sc.total;
-                // u1 (selection, kmc_events.cu:469) and u2 (residence time, :515) were drawn by warp 1 during the
-                // previous event's S phase (or at start-up): the generator is off the critical path
-                const double u1 = s_upair[s_nevents & 1][0];
-                if (lane == 0) {
-                    s_u2 = s_upair[s_nevents & 1][1];
-                    s_psum = Psum;
-                }
+                Psum = sc.total;
+                // u1 (selection, kmc_events.cu:469) and -log(u2) (residence time, :515) were drawn two events ago
+                const double u1 = s_u1[e & 3];
                 double number = u1 * Psum;
-                double prev;
+                double prev, cur;
                 int ts = (Psum > 0.0) ? warp_pick_256(sc, v, number, &prev) : -1;
-                EV_TICK(8);
+                W_TICK(13);
                 int r = -1;  // all slot indices fit 32 bits: N * nn <= 16.7 M * 64 < 2^31
+                bool spec = false;
                 if (ts >= 0) {
                     number = number - prev;
+                    pos = prev;
                     // ---- chunk level: stored prefixes of super ts ---------------------------------------------
                     double inc[8];
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) inc[k] = ci[ts * 256 + 8 * lane + k];
-                    int tc = warp_pick_incl(inc, number, &prev, [&](double *vv) {
+                    for (int k = 0; k < 8; ++k) inc[k] = ci[KMC_CS(ts, k)];
+                    int tc = warp_pick_incl(inc, number, &prev, &cur, [&](double *vv) {
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) vv[k] = cs[ts * 256 + 8 * lane + k];
+                        for (int k = 0; k < 8; ++k) vv[k] = cs[KMC_CS(ts, k)];
                     });
-                    EV_TICK(9);
+                    W_TICK(4);
                     if (tc >= 0) {
                         number = number - prev;
+                        pos = pos + prev;
                         const int chunk = ts * 256 + tc;
-                        // ---- row level: stored prefixes of the chunk (one L2 round trip) ------------------------
+                        // ---- row level: stored prefixes of the chunk: the predictor's copy, else one round trip ------
+                        if (a.use_spec) {
+                            while (*(volatile int *)&s_spec_ready < e) { }
+                            __threadfence_block();
+                            spec = (*(volatile int *)&s_spec_valid != 0) && (*(volatile int *)&s_spec_chunk == chunk);
+                        }
                         const int rbase = chunk * 256 + 8 * lane;
-                        {
+                        if (spec) {
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) inc[k] = s_spec_incl[32 * k + lane];
+                        } else {
                             const double2 *src2 = reinterpret_cast<const double2 *>(a.rowincl + rbase);
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
@@ -502,13 +566,15 @@ __global__ void __launch_bounds__(EV_THREADS, 1) event_loop_kernel(EvLoopArgs a)
                                 inc[2 * k] = t2.x; inc[2 * k + 1] = t2.y;
                             }
                         }
-                        int tr = warp_pick_incl(inc, number, &prev, [&](double *vv) {
+                        int tr = warp_pick_incl(inc, number, &prev, &cur, [&](double *vv) {
 #pragma unroll
                             for (int k = 0; k < 8; ++k) vv[k] = (rbase + k < a.N) ? a.rowsum[rbase + k] : 0.0;
                         });
-                        EV_TICK(10);
+                        W_TICK(5);
                         if (tr >= 0) {
                             number = number - prev;
+                            pos = pos + prev;
+                            wrow = cur - prev;
                             r = chunk * 256 + tr;
                         }
                     }
@@ -516,14 +582,23 @@ __global__ void __launch_bounds__(EV_THREADS, 1) event_loop_kernel(EvLoopArgs a)
                 if (r >= 0) {
                     // ---- slot level: lanes hold slots lane and lane+32; walk the non-zero slots in order --------
                     const int base = r * nn;
-                    if (lane < 2) prefetch_l2(a.rev + r * REV_STRIDE + 32 * lane);  // for the zero-out phase
                     double p0 = 0.0, p1 = 0.0;
                     int nb0 = -1, nb1 = -1, ty0 = KMCB200_NULL_EVENT, ty1 = KMCB200_NULL_EVENT;
-                    if (lane < nn) { p0 = a.prob[base + lane]; nb0 = a.neigh[base + lane]; ty0 = a.type[base + lane]; }
-                    if (lane + 32 < nn) { p1 = a.prob[base + lane + 32]; nb1 = a.neigh[base + lane + 32]; ty1 = a.type[base + lane + 32]; }
-                    // every candidate partner's reverse-index row starts its trip from DRAM now (the zero-out needs one)
-                    if (p0 > 0.0) { prefetch_l2(a.rev + nb0 * REV_STRIDE); prefetch_l2(a.rev + nb0 * REV_STRIDE + 32); }
-                    if (p1 > 0.0) { prefetch_l2(a.rev + nb1 * REV_STRIDE); prefetch_l2(a.rev + nb1 * REV_STRIDE + 32); }
+                    if (spec && *(volatile int *)&s_spec_r == r) {
+                        p0 = s_spec_p[lane]; p1 = s_spec_p[lane + 32];
+                        nb0 = s_spec_nb[lane]; nb1 = s_spec_nb[lane + 32];
+                        ty0 = s_spec_ty[lane]; ty1 = s_spec_ty[lane + 32];
+#ifdef KMC_EV_PROFILE
+                        if (lane == 0) atomicAdd(&s_prof[15], 1ull);
+#endif
+                    } else {
+                        if (lane < 2) prefetch_l2(a.rev + r * REV_STRIDE + 32 * lane);  // for the zero-out phase
+                        if (lane < nn) { p0 = a.prob[base + lane]; nb0 = a.neigh[base + lane]; ty0 = a.type[base + lane]; }
+                        if (lane + 32 < nn) { p1 = a.prob[base + lane + 32]; nb1 = a.neigh[base + lane + 32]; ty1 = a.type[base + lane + 32]; }
+                        // every candidate partner's reverse-index row starts its trip from DRAM now (the zero-out needs one)
+                        if (p0 > 0.0) { prefetch_l2(a.rev + nb0 * REV_STRIDE); prefetch_l2(a.rev + nb0 * REV_STRIDE + 32); }
+                        if (p1 > 0.0) { prefetch_l2(a.rev + nb1 * REV_STRIDE); prefetch_l2(a.rev + nb1 * REV_STRIDE + 32); }
+                    }
                     unsigned m0 = __ballot_sync(KMC_FULL_MASK, p0 > 0.0), m1 = __ballot_sync(KMC_FULL_MASK, p1 > 0.0);
                     int seln = -1, lastn = -1;
                     double acc = 0.0;
@@ -538,7 +613,7 @@ __global__ void __launch_bounds__(EV_THREADS, 1) event_loop_kernel(EvLoopArgs a)
                         if (acc > number) { seln = n; break; }
                     }
                     if (seln < 0) seln = lastn;
-                    EV_TICK(11);
+                    W_TICK(6);
                     if (seln >= 0) {
                         ej = __shfl_sync(KMC_FULL_MASK, (seln < 32) ? nb0 : nb1, seln & 31);
                         ety = __shfl_sync(KMC_FULL_MASK, (seln < 32) ? ty0 : ty1, seln & 31);
@@ -549,147 +624,258 @@ __global__ void __launch_bounds__(EV_THREADS, 1) event_loop_kernel(EvLoopArgs a)
             }
             if (lane == 0) {
                 s_stop = !go;
-                s_i = ei; s_j = ej; s_ty = ety; s_slot = eslot;
-                n_rows = 0;
+                if (go) {
+                    EvRecord &rec = s_rec[e & 1];
+                    rec.i = ei; rec.j = ej; rec.ty = ety; rec.slot = eslot; rec.psum = Psum;
+                    rec.pos = pos; rec.w = wrow;
+                    s_event_time = s_lg[e & 3] / Psum;  // residence time (kmc_events.cu:515)
+                    s_nevents = e + 1;
+                }
                 n_chunks = 0;
-                n_supers = 0;
+                n_rows = 0;
             }
         }
-        __syncthreads();
+        __syncthreads();  // ---- barrier A
         EV_TICK(0);
         if (s_stop) break;
-        const int ei = s_i, ej = s_j;
-        // =============================== Z: zero-out + apply + residence time ================================
-        if (tid == EV_THREADS - 1) {  // residence time (kmc_events.cu:515)
-            s_event_time = -log(s_u2) / s_psum;
-            s_nevents = s_nevents + 1;
-        }
-        if (ei >= 0) {
-            if (tid == EV_THREADS - 32) {  // execute_event: kmc_events.cu:305-328
-                const int i = ei, j = ej, ty = s_ty;
-                if (ty == KMCB200_VACANCY_GENERATION) {
-                    a.element[i] = KMCB200_OXYGEN_DEFECT; a.element[j] = KMCB200_VACANCY;
-                    a.charge[i] = -2; a.charge[j] = 2;
-                } else if (ty == KMCB200_VACANCY_RECOMBINATION) {
-                    a.element[i] = KMCB200_DEFECT; a.element[j] = KMCB200_O;
-                    a.charge[i] = 0; a.charge[j] = 0;
-                } else if (ty == KMCB200_VACANCY_DIFFUSION || ty == KMCB200_ION_DIFFUSION) {
-                    int e_i = a.element[i], e_j = a.element[j], q_i = a.charge[i], q_j = a.charge[j];
-                    a.element[i] = e_j; a.element[j] = e_i;
-                    a.charge[i] = q_j; a.charge[j] = q_i;
+        const int ev_idx = s_nevents - 1;
+        const int ei = s_rec[ev_idx & 1].i, ej = s_rec[ev_idx & 1].j;
+        // =============================== P (part 1): predict the next event's chunk from the UNREPAIRED sums ==========
+        int pchunk = -1;
+        double pnum = 0.0, pinc[8];
+        if (warp == PW && a.use_spec) {
+            const EvRecord rec = s_rec[ev_idx & 1];
+            if (rec.i >= 0) {
+                Scan256 sc;
+                double v[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { v[k] = ss[32 * k + lane]; sc.a[k] = v[k]; }
+                warp_scan_256(sc);
+                // the point the next draw will land on, in the coordinates of the sums BEFORE this event's repair: the
+                // event removes (to first order) row i's total rate w, which sits at cumulative position pos
+                double t = s_u1[(ev_idx + 1) & 3] * (rec.psum - rec.w);
+                if (t >= rec.pos) t = t + rec.w;
+                double prev, cur;
+                const int ts = warp_pick_256(sc, v, t, &prev);
+                if (ts >= 0) {
+                    t = t - prev;
+                    double inc[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) inc[k] = ci[KMC_CS(ts, k)];
+                    const int tc = warp_pick_incl(inc, t, &prev, &cur, [&](double *vv) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) vv[k] = cs[KMC_CS(ts, k)];
+                    });
+                    if (tc >= 0) {
+                        pnum = t - prev;
+                        pchunk = ts * 256 + tc;
+                        const double2 *src2 = reinterpret_cast<const double2 *>(a.rowincl + pchunk * 256 + 8 * lane);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {  // in flight across the barriers below
+                            double2 t2 = src2[k];
+                            pinc[2 * k] = t2.x; pinc[2 * k + 1] = t2.y;
+                        }
+                    }
                 }
             }
-            // zero-out (zero_out_events_split, kmc_events.cu:247-266).  Padded slots already hold rate 0 / NULL_EVENT,
-            // so rows ei and ej are cleared entirely; slots of other rows pointing at ei / ej come from the reverse index.
-            if (tid < 2 * REV_STRIDE) {
-                const int which = tid / REV_STRIDE, q = tid % REV_STRIDE;
-                const int s_site = which ? ej : ei;
-                if (q < nn) {
-                    const int sl = s_site * nn + q;
+            if (lane == 0) {
+                s_spec_chunk = pchunk;
+                s_spec_valid = (pchunk >= 0);  // cleared in R2 if a row of this chunk changes in the current event
+            }
+        }
+        // =============================== Z: zero-out ================================================================
+        // zero_out_events_split (kmc_events.cu:247-266): every slot whose row or neighbour is i or j.  Padded slots
+        // already hold rate 0 / NULL_EVENT, so rows i and j are cleared entirely; slots of other rows pointing at i / j
+        // come from the reverse index.  4 warps (one per scheduler): the phase is two dependent round trips, not work.
+        if (ei >= 0 && tid < 2 * REV_STRIDE) {
+            const int s_site = (tid < REV_STRIDE) ? ei : ej;
+            const int q = tid & (REV_STRIDE - 1);
+            const int packed = a.rev[s_site * REV_STRIDE + q];
+            if (q < nn) {  // the event's own rows
+                const int sl = s_site * nn + q;
+                a.prob[sl] = 0.0;
+                a.type[sl] = KMCB200_NULL_EVENT;
+            }
+            if (q == 0) {  // ... whose sums become +0.0
+                a.rowsum[s_site] = 0.0;
+                const int c = s_site >> 8;
+                const unsigned bit = 1u << (c & 31);
+                if (!(atomicOr(&chunk_bits[c >> 5], bit) & bit)) {
+                    chunk_list[atomicAdd(&n_chunks, 1)] = c;
+                    if (atomicAdd(&super_cnt[c >> 8], 1) == 0) atomicAdd(&n_supers, 1);
+                }
+            }
+            if (packed >= 0) {
+                const int rr = packed >> 6;
+                const int sl = rr * nn + (packed & 63);
+                // a slot that already holds rate 0 does not change its row: only rows that lose a non-zero rate need
+                // their sums repaired (their recomputed sums would be bit-identical anyway)
+                const double oldp = a.prob[sl];
+                a.type[sl] = KMCB200_NULL_EVENT;
+                if (oldp != 0.0) {
                     a.prob[sl] = 0.0;
-                    a.type[sl] = KMCB200_NULL_EVENT;
+                    if (rr != ei && rr != ej) rows_list[atomicAdd(&n_rows, 1)] = rr;
                 }
-                const int packed = a.rev[s_site * REV_STRIDE + q];
-                int rr = -1;
-                if (packed >= 0) {
-                    const int sl = (packed >> 6) * nn + (packed & 63);
-                    // a slot that already holds rate 0 does not change its row: only rows that lose a non-zero rate need
-                    // their sums repaired (their recomputed sums would be bit-identical anyway)
-                    double oldp = a.prob[sl];
-                    a.type[sl] = KMCB200_NULL_EVENT;
-                    if (oldp != 0.0) {
-                        a.prob[sl] = 0.0;
-                        rr = packed >> 6;
-                    }
-                } else if (q == REV_STRIDE - 1) {
-                    rr = s_site;  // the event's own rows (their sums become 0)
-                }
-                if (rr >= 0) {
-                    int pos = atomicAdd(&n_rows, 1);
-                    rows_list[pos] = rr;
-                    if (smem_set_insert(chunk_set, 1023, rr >> 8)) {
-                        chunk_list[atomicAdd(&n_chunks, 1)] = rr >> 8;
-                        if (atomicExch(&super_flag[rr >> 16], 1) == 0) super_list[atomicAdd(&n_supers, 1)] = rr >> 16;
+            }
+        }
+        __syncthreads();  // ---- barrier B1
+        EV_TICK(1);
+        // =============================== R1: row sums, one warp per row that lost a rate ===========================
+        // (a row listed twice -- it lost a rate to i and one to j -- is recomputed twice with the same result)
+        if (warp < NCW) {
+            const int nd = n_rows;
+            for (int qq = warp; qq < nd; qq += NCW) {
+                const int rr = rows_list[qq];
+                const int pb = rr * nn;
+                const double p0 = (lane < nn) ? a.prob[pb + lane] : 0.0;
+                const double p1 = (lane + 32 < nn) ? a.prob[pb + lane + 32] : 0.0;
+                const double sacc = warp_row_sum(p0, p1);
+                if (lane == 0) {
+                    a.rowsum[rr] = sacc;
+                    const int c = rr >> 8;
+                    const unsigned bit = 1u << (c & 31);
+                    if (!(atomicOr(&chunk_bits[c >> 5], bit) & bit)) {
+                        chunk_list[atomicAdd(&n_chunks, 1)] = c;
+                        if (atomicAdd(&super_cnt[c >> 8], 1) == 0) atomicAdd(&n_supers, 1);
                     }
                 }
             }
         }
-        __syncthreads();
-        EV_TICK(1);
-        if (ei >= 0) {
-            if (tid == 0) {  // event log (i, j, type, slot) + Psum before the event
-                int ne = s_nevents - 1;
-                if (ne < a.log_cap) {
-                    a.log[4 * ne + 0] = ei; a.log[4 * ne + 1] = ej; a.log[4 * ne + 2] = s_ty; a.log[4 * ne + 3] = s_slot;
-                    a.log_psum[ne] = s_psum;
+        __syncthreads();  // ---- barrier B2
+        EV_TICK(3);
+        // =============================== R2 / H / P: repair, housekeeping, speculation; election of the next selector =
+        i_select = false;
+        const int nc = n_chunks;
+        if (warp == PW) {
+            if (a.use_spec) {
+                // ---- P (part 2): the predicted row inside the predicted chunk, its slots -> shared memory ----------
+                int pr = -1;
+                if (pchunk >= 0) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) s_spec_incl[32 * k + lane] = pinc[k];
+                    double prev, cur;
+                    const int rbase = pchunk * 256 + 8 * lane;
+                    const int tr = warp_pick_incl(pinc, pnum, &prev, &cur, [&](double *vv) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) vv[k] = (rbase + k < a.N) ? a.rowsum[rbase + k] : 0.0;
+                    });
+                    if (tr >= 0) {
+                        pr = pchunk * 256 + tr;
+                        const int base = pr * nn;
+                        double p0 = 0.0, p1 = 0.0;
+                        int nb0 = -1, nb1 = -1, ty0 = KMCB200_NULL_EVENT, ty1 = KMCB200_NULL_EVENT;
+                        if (lane < 2) prefetch_l2(a.rev + pr * REV_STRIDE + 32 * lane);
+                        if (lane < nn) { p0 = a.prob[base + lane]; nb0 = a.neigh[base + lane]; ty0 = a.type[base + lane]; }
+                        if (lane + 32 < nn) { p1 = a.prob[base + lane + 32]; nb1 = a.neigh[base + lane + 32]; ty1 = a.type[base + lane + 32]; }
+                        if (p0 > 0.0) { prefetch_l2(a.rev + nb0 * REV_STRIDE); prefetch_l2(a.rev + nb0 * REV_STRIDE + 32); }
+                        if (p1 > 0.0) { prefetch_l2(a.rev + nb1 * REV_STRIDE); prefetch_l2(a.rev + nb1 * REV_STRIDE + 32); }
+                        s_spec_p[lane] = p0; s_spec_p[lane + 32] = p1;
+                        s_spec_nb[lane] = nb0; s_spec_nb[lane + 32] = nb1;
+                        s_spec_ty[lane] = ty0; s_spec_ty[lane + 32] = ty1;
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    s_spec_r = pr;
+                    __threadfence_block();
+                    *(volatile int *)&s_spec_ready = ev_idx + 1;
                 }
             }
-            const int nd = n_rows, nc = n_chunks;
-            for (int q = tid; q < 1024; q += EV_THREADS) chunk_set[q] = -1;  // next use: the next event's Z phase
-#ifdef KMC_EV_PROFILE
-            if (tid == 0) { ph[14] += nd; ph[15] += nc; }
-#endif
-            // =============================== R1: row sums, one warp per touched row ==================================
-            // (duplicates in rows_list recompute the same value)
-            for (int q = warp; q < nd; q += NW) {
-                const int rr = rows_list[q];
-                const int pb = rr * nn;
-                double p0 = (lane < nn) ? a.prob[pb + lane] : 0.0;
-                double p1 = (lane + 32 < nn) ? a.prob[pb + lane + 32] : 0.0;
-                double sacc = warp_row_sum(p0, p1);
-                if (lane == 0) a.rowsum[rr] = sacc;
+        } else if (warp == HW) {
+            // ---- H: event application, log, uniforms of event ev_idx + 2 -----------------------------------------
+            if (lane == 0) {
+                const EvRecord rec = s_rec[ev_idx & 1];
+                if (rec.i >= 0) {  // execute_event: kmc_events.cu:305-328
+                    const int i = rec.i, j = rec.j, ty = rec.ty;
+                    if (ty == KMCB200_VACANCY_GENERATION) {
+                        a.element[i] = KMCB200_OXYGEN_DEFECT; a.element[j] = KMCB200_VACANCY;
+                        a.charge[i] = -2; a.charge[j] = 2;
+                    } else if (ty == KMCB200_VACANCY_RECOMBINATION) {
+                        a.element[i] = KMCB200_DEFECT; a.element[j] = KMCB200_O;
+                        a.charge[i] = 0; a.charge[j] = 0;
+                    } else if (ty == KMCB200_VACANCY_DIFFUSION || ty == KMCB200_ION_DIFFUSION) {
+                        int e_i = a.element[i], e_j = a.element[j], q_i = a.charge[i], q_j = a.charge[j];
+                        a.element[i] = e_j; a.element[j] = e_i;
+                        a.charge[i] = q_j; a.charge[j] = q_i;
+                    }
+                    if (ev_idx < a.log_cap) {  // event log (i, j, type, slot) + Psum before the event
+                        a.log[4 * ev_idx + 0] = rec.i; a.log[4 * ev_idx + 1] = rec.j;
+                        a.log[4 * ev_idx + 2] = rec.ty; a.log[4 * ev_idx + 3] = rec.slot;
+                        a.log_psum[ev_idx] = rec.psum;
+                    }
+                }
+                const int e2 = ev_idx + 2;
+                s_u1[e2 & 3] = evrng_next_double(rng);
+                s_lg[e2 & 3] = -log(evrng_next_double(rng));
             }
-            __syncthreads();
-            EV_TICK(2);
-            // =============================== R2: one warp per touched chunk: scan_256 of its 256 row sums; the total goes
-            // to the chunk sums, the inclusive prefixes to rowincl (what the selector's row level compares against) ======
-            for (int q = warp; q < nc; q += NW) {
-                const int c = chunk_list[q];
+        } else {
+            if (nc == 0) i_select = (warp == 0);  // nothing changed (no selectable event): warp 0 selects again
+            if (warp == 0) W_START();
+            for (int qq = warp; qq < nc; qq += NCW) {
+                const int c = chunk_list[qq];
                 Scan256 sc;
                 const double2 *src2 = reinterpret_cast<const double2 *>(a.rowsum + c * 256 + 8 * lane);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) { double2 t2 = src2[k]; sc.a[2 * k] = t2.x; sc.a[2 * k + 1] = t2.y; }
+                if (warp == 0) { if (__any_sync(KMC_FULL_MASK, sc.a[0] == -1.2345)) s_stop = 2; W_TICK(10); }
                 warp_scan_256(sc);
-                if (lane == 0) {
-                    cs[c] = sc.total;
-                    if (SMEM) a.chunksum[c] = sc.total;
-                }
+                if (warp == 0) W_TICK(11);
                 double2 *dst2 = reinterpret_cast<double2 *>(a.rowincl + c * 256 + 8 * lane);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) dst2[k] = make_double2(scan_incl(sc, 2 * k), scan_incl(sc, 2 * k + 1));
-            }
-            __syncthreads();
-            EV_TICK(4);
-            // =============================== U: one warp per touched super: scan_256 of its chunk sums ===============
-            const int nsd = n_supers;
-            for (int q = warp; q < nsd; q += NW) {
-                const int sidx = super_list[q];
-                Scan256 su;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) su.a[k] = cs[sidx * 256 + 8 * lane + k];
-                warp_scan_256(su);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) ci[sidx * 256 + 8 * lane + k] = scan_incl(su, k);
+                const int sidx = c >> 8;
+                int left = 0;
                 if (lane == 0) {
-                    ss[sidx] = su.total;
-                    a.supersum[sidx] = su.total;
-                    super_flag[sidx] = 0;
+                    cs[KMC_CIDX(c)] = sc.total;
+                    chunk_bits[c >> 5] = 0u;  // every set bit of this word belongs to a dirty chunk handled in this phase
+                    if (c == s_spec_chunk) s_spec_valid = 0;  // the predictor's copies of this chunk are stale
+                    __threadfence_block();
+                    left = atomicSub(&super_cnt[sidx], 1) - 1;
+                }
+                left = __shfl_sync(KMC_FULL_MASK, left, 0);
+                if (warp == 0) W_TICK(12);
+                if (left == 0) {
+                    // ---- this warp finished the last dirty chunk of super sidx: re-scan the super -------------
+                    __threadfence_block();
+                    Scan256 su;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) su.a[k] = cs[KMC_CS(sidx, k)];
+                    warp_scan_256(su);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) ci[KMC_CS(sidx, k)] = scan_incl(su, k);
+                    int sleft = 0;
+                    if (lane == 0) {
+                        ss[tpos(sidx)] = su.total;
+                        __threadfence_block();
+                        sleft = atomicSub(&n_supers, 1) - 1;
+                    }
+                    sleft = __shfl_sync(KMC_FULL_MASK, sleft, 0);
+                    if (sleft == 0) {  // ... and the last dirty super: this warp selects the next event
+                        __threadfence_block();
+                        i_select = true;
+                    }
                 }
             }
-            __syncthreads();
-            EV_TICK(3);
         }
+        EV_TICK(2);
     }
-    // the pair drawn for the event that did not happen is handed back to the generator
-    for (int q = tid; q < 624; q += EV_THREADS) a.mt_state[q] = s_backup_valid ? mt_backup[q] : mt[q];
+#undef KMC_CIDX
+#undef KMC_CS
+    // hand the generator back exactly 4 words per executed event in (the uniforms drawn ahead are returned)
+    {
+        const long long consumed = 4ll * s_nevents;
+        const bool curblk = consumed >= rng.block_start;
+        const unsigned *src = curblk ? rng.mt : rng.backup;
+        for (int q = tid; q < 624; q += EV_THREADS) a.mt_state[q] = src[q];
+        if (tid == 0) a.mt_state[624] = (unsigned)(consumed - (curblk ? rng.block_start : rng.prev_block_start));
+    }
     if (tid == 0) {
-        a.mt_state[624] = (unsigned)s_pos_before;
         a.result->event_time = s_event_time;
-        a.result->psum_last = s_psum;
+        a.result->psum_last = s_nevents > 0 ? s_rec[(s_nevents - 1) & 1].psum : 0.0;
         a.result->n_events = s_nevents;
-        a.result->error = s_error;
+        a.result->error = 0;
 #ifdef KMC_EV_PROFILE
-        if (a.phase_cycles) for (int q = 0; q < 16; ++q) a.phase_cycles[q] = ph[q];
+        if (a.phase_cycles) for (int q = 0; q < 16; ++q) a.phase_cycles[q] = (q >= 4) ? (long long)s_prof[q] : ph[q];
 #endif
     }
 }
@@ -723,10 +909,9 @@ extern "C" int kmcb200_events_create(kmcb200_ctx *ctx, int N, int nn, const int 
     auto A = [&](void **p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
     A((void **)&ev->prob, (size_t)total * sizeof(double));
     A((void **)&ev->type, (size_t)total);
-    A((void **)&ev->rowsum, (size_t)ev->nchunk * 256 * sizeof(double));  // padded to whole chunks (tail stays 0)
+    A((void **)&ev->rowsum, (size_t)ev->nchunk * 256 * 2 * sizeof(double));  // rowsum | rowincl, padded to whole chunks (tail stays 0)
     A((void **)&ev->chunksum, (size_t)ev->nsuper * 256 * sizeof(double));  // padded to whole supers (tail stays 0)
     A((void **)&ev->supersum, (size_t)MAX_SUPER * sizeof(double));
-    A((void **)&ev->rowincl, (size_t)ev->nchunk * 256 * sizeof(double));
     A((void **)&ev->chunkincl, (size_t)ev->nsuper * 256 * sizeof(double));
     A((void **)&ev->mt, 640 * sizeof(unsigned));
     A((void **)&ev->log, (size_t)ev->log_cap * 4 * sizeof(int));
@@ -736,6 +921,22 @@ extern "C" int kmcb200_events_create(kmcb200_ctx *ctx, int N, int nn, const int 
         kmc_set_error("cudaMalloc failed in events_create: %s", cudaGetErrorString(e));
         kmcb200_events_destroy(ev);
         return KMCB200_E_CUDA;
+    }
+    ev->rowincl = ev->rowsum + (size_t)ev->nchunk * 256;
+    {   // persisting-L2 window over rowsum | rowincl (see kmcb200_execute_kmc_step)
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, ctx->device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0 &&
+            prop.accessPolicyMaxWindowSize > 0) {
+            size_t want = (size_t)ev->nchunk * 256 * 2 * sizeof(double);
+            size_t setaside = want < (size_t)prop.persistingL2CacheMaxSize ? want : (size_t)prop.persistingL2CacheMaxSize;
+            if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, setaside) == cudaSuccess) {
+                ev->l2_window_bytes = want < (size_t)prop.accessPolicyMaxWindowSize ? want : (size_t)prop.accessPolicyMaxWindowSize;
+                ev->l2_hit_ratio = (float)((double)setaside / (double)ev->l2_window_bytes);
+                if (ev->l2_hit_ratio > 1.0f) ev->l2_hit_ratio = 1.0f;
+            } else {
+                cudaGetLastError();
+            }
+        }
     }
     // reverse neighbour index: for each site s the slots (r,n) with neigh[r][n] == s (static)
     int *fill = nullptr;
@@ -747,7 +948,7 @@ extern "C" int kmcb200_events_create(kmcb200_ctx *ctx, int N, int nn, const int 
         return KMCB200_E_CUDA;
     }
     cudaMemsetAsync(ev->rev, 0xff, (size_t)N * REV_STRIDE * sizeof(int), ctx->stream);
-    cudaMemsetAsync(ev->rowsum, 0, (size_t)ev->nchunk * 256 * sizeof(double), ctx->stream);
+    cudaMemsetAsync(ev->rowsum, 0, (size_t)ev->nchunk * 256 * 2 * sizeof(double), ctx->stream);
     cudaMemsetAsync(ev->chunksum, 0, (size_t)ev->nsuper * 256 * sizeof(double), ctx->stream);
     cudaMemsetAsync(fill, 0, (size_t)(N + 2) * sizeof(int), ctx->stream);
     unsigned blocks = (unsigned)((total + 255) / 256);
@@ -773,7 +974,7 @@ extern "C" int kmcb200_events_destroy(kmcb200_events *ev) {
     if (!ev) return 0;
     if (ev->ctx) cudaStreamSynchronize(ev->ctx->stream);
     cudaFree(ev->prob); cudaFree(ev->type); cudaFree(ev->rowsum); cudaFree(ev->chunksum); cudaFree(ev->supersum);
-    cudaFree(ev->rowincl); cudaFree(ev->chunkincl);
+    cudaFree(ev->chunkincl);
     cudaFree(ev->rev); cudaFree(ev->mt); cudaFree(ev->log); cudaFree(ev->log_psum);
     cudaFree(ev->result);
     delete ev;
@@ -880,29 +1081,49 @@ extern "C" int kmcb200_execute_kmc_step(kmcb200_ctx *ctx, kmcb200_events *ev, in
     a.log = ev->log; a.log_psum = ev->log_psum; a.log_cap = ev->log_cap;
     a.result = ev->result;
     a.phase_cycles = nullptr;
+    a.use_spec = getenv("KMCB200_EV_NO_SPEC") ? 0 : 1;  // tests run both: results must not depend on it
 #ifdef KMC_EV_PROFILE
     KMC_TRY(kmc_scratch(ctx, 5, 16 * sizeof(long long), (void **)&a.phase_cycles));
 #endif
     // chunk sums + their stored prefixes live in shared memory when they fit (up to ~3.2 M sites); larger devices
     // read them from L2
     size_t dyn = (size_t)(2 * ev->nsuper * 256) * sizeof(double);
-    a.chunks_in_smem = dyn <= 190 * 1024 ? 1 : 0;
-    if (getenv("KMCB200_EV_NO_SMEM")) a.chunks_in_smem = 0;  // tests: exercise the large-device (> 3.2 M sites) path
-    if (a.chunks_in_smem && ctx->smem_cfg_events == 0) {
+    bool chunks_in_smem = dyn <= 190 * 1024;
+    if (getenv("KMCB200_EV_NO_SMEM")) chunks_in_smem = false;  // tests: exercise the large-device (> 3.2 M sites) path
+    if (chunks_in_smem && ctx->smem_cfg_events == 0) {
         KMC_CUDA(cudaFuncSetAttribute(event_loop_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(190 * 1024)));
         ctx->smem_cfg_events = 190 * 1024;
     }
+    // The row sums and their stored prefixes (one allocation, 16 B per site) are what the loop re-reads at random for
+    // every event; pin them in the persisting part of L2 for the duration of the loop so that the selector's row level
+    // and the chunk re-scan are L2 hits instead of DRAM round trips.
+    const bool persist = ev->l2_window_bytes > 0 && !getenv("KMCB200_EV_NO_L2_PERSIST");
+    if (persist) {
+        cudaStreamAttrValue attr;
+        memset(&attr, 0, sizeof(attr));
+        attr.accessPolicyWindow.base_ptr = ev->rowsum;
+        attr.accessPolicyWindow.num_bytes = ev->l2_window_bytes;
+        attr.accessPolicyWindow.hitRatio = ev->l2_hit_ratio;
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        KMC_CUDA(cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+    }
     kmc_count_launch();
-    if (a.chunks_in_smem) event_loop_kernel<true><<<1, EV_THREADS, dyn, ctx->stream>>>(a);
+    if (chunks_in_smem) event_loop_kernel<true><<<1, EV_THREADS, dyn, ctx->stream>>>(a);
     else event_loop_kernel<false><<<1, EV_THREADS, 0, ctx->stream>>>(a);
     KMC_CUDA(cudaGetLastError());
+    if (persist) {
+        cudaStreamAttrValue attr;
+        memset(&attr, 0, sizeof(attr));
+        attr.accessPolicyWindow.num_bytes = 0;  // no window for whatever is launched on this stream next
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyNormal;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+        KMC_CUDA(cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+    }
     EvResult *h = (EvResult *)ctx->h_mail;
     KMC_CUDA(cudaMemcpyAsync(h, ev->result, sizeof(EvResult), cudaMemcpyDeviceToHost, ctx->stream));
     KMC_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (h->error) {
-        kmc_set_error("event loop: more than %d touched rows in one event", MAX_DIRTY);
-        return KMCB200_E_CAPACITY;
-    }
+    if (persist) cudaCtxResetPersistingL2Cache();  // the pinned lines go back to normal replacement
 #ifdef KMC_EV_PROFILE
     {
         long long ph[16];
