@@ -81,10 +81,12 @@ SIGNATURES = {
     "kmcb200_set_stream": (_i, [_vp, _vp]),
     "kmcb200_synchronize": (_i, [_vp]),
     "kmcb200_device_info": (_i, [_vp, _pi, _pi, _pi, C.POINTER(C.c_size_t)]),
+    "kmcb200_fp64_peak": (_i, [_vp, _pd]),
     "kmcb200_malloc": (_i, [_vp, _pvp, C.c_size_t]),
     "kmcb200_free": (_i, [_vp, _vp]),
     "kmcb200_memcpy_h2d": (_i, [_vp, _vp, _vp, C.c_size_t]),
     "kmcb200_memcpy_d2h": (_i, [_vp, _vp, _vp, C.c_size_t]),
+    "kmcb200_memcpy_d2d": (_i, [_vp, _vp, _vp, C.c_size_t]),
     "kmcb200_memset": (_i, [_vp, _vp, _i, C.c_size_t]),
     "kmcb200_host_alloc_pinned": (_i, [_pvp, C.c_size_t]),
     "kmcb200_host_free_pinned": (_i, [_vp]),
@@ -114,7 +116,7 @@ SIGNATURES = {
     "kmcb200_comm_set_send_masks": (_i, [_vp, _vp]),
     "kmcb200_comm_info": (_i, [_vp, _pi, _pi, C.POINTER(C.c_uint), _pll]),
     "kmcb200_poisson_gridless": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _d, _d, _d, _i, _i, _vp]),
-    "kmcb200_poisson_stats": (_i, [_vp, _pll, _pll]),
+    "kmcb200_poisson_stats": (_i, [_vp, _pll, _pll, _pll]),
     "kmcb200_sum_potential": (_i, [_vp, _i, _vp, _vp]),
     "kmcb200_events_create": (_i, [_vp, _i, _i, _vp, _pvp]),
     "kmcb200_events_destroy": (_i, [_vp]),
@@ -285,6 +287,11 @@ class Context:
     def sync(self):
         _check(self.lib.kmcb200_synchronize(self.h))
 
+    def fp64_peak_tflops(self) -> float:
+        out = C.c_double(0)
+        _check(self.lib.kmcb200_fp64_peak(self.h, C.byref(out)))
+        return out.value
+
     # -- tensor helpers
     def dev_i(self, a):
         return self.torch.as_tensor(_np_i(a), device=self.device)
@@ -412,9 +419,10 @@ class Context:
                                                  sigma, k, cutoff, row_start, row_count, _ptr(pot_charge)))
 
     def poisson_stats(self):
-        a, b = C.c_longlong(0), C.c_longlong(0)
-        _check(self.lib.kmcb200_poisson_stats(self.h, C.byref(a), C.byref(b)))
-        return a.value, b.value
+        """(charged sources, distance tests, pairs inside the cutoff) of the last poisson_gridless call"""
+        a, b, c = C.c_longlong(0), C.c_longlong(0), C.c_longlong(0)
+        _check(self.lib.kmcb200_poisson_stats(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
 
     def sum_potential(self, pot_charge, pot_boundary):
         _check(self.lib.kmcb200_sum_potential(self.h, pot_charge.numel(), _ptr(pot_charge), _ptr(pot_boundary)))
@@ -467,6 +475,17 @@ class KMatrix:
                 "inv_diag": self._copy_out(dinv, self.rows, np.float64),
                 "rhs": self._copy_out(rhs, self.rows, np.float64),
             })
+        return out
+
+    def device_vectors(self):
+        """(inv_diag, rhs) of the last assemble_K as torch tensors (device-to-device copies of the kmat's arrays)"""
+        ctx = self.ctx
+        ptrs = self._raw_pointers()
+        out = []
+        for ptr in (ptrs[7], ptrs[8]):
+            t = ctx.empty_d(self.rows)
+            _check(ctx.lib.kmcb200_memcpy_d2d(ctx.h, _ptr(t), C.c_void_p(ptr), self.rows * 8))
+            out.append(t)
         return out
 
     def block_view(self, col_start, col_count):

@@ -61,6 +61,7 @@ struct kmcb200_ctx {
     // coulomb statistics of the last call
     long long last_num_charged = 0, last_pair_tests = 0;
     void *pair_counter_dev = nullptr;
+    void *coulomb_plan = nullptr;  // CoulombPlan (coulomb.cu), owned by the context
     // dot/pcg workspace
     CgState *cg_state = nullptr;  // device
     bool cg_done_stale = false;   // a PCG solve ended abnormally: CgState::done may still be set
@@ -71,6 +72,7 @@ struct kmcb200_ctx {
 };
 
 int kmc_scratch(kmcb200_ctx *ctx, int slot, size_t bytes, void **out);
+void kmc_coulomb_plan_free(kmcb200_ctx *ctx);  // coulomb.cu
 
 // ---- device helpers -------------------------------------------------------------------------------
 // gpu_solvers.h:280-285 (reference): sqrt(pow(dx,2)+pow(dy,2)+pow(dz,2)); products and sums rounded

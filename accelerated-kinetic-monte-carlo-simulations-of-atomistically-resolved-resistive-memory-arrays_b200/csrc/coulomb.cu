@@ -233,6 +233,7 @@ __global__ void __launch_bounds__(CT) coulomb_cell_kernel(const double *__restri
     if (active) { xi = x[i]; yi = y[i]; zi = z[i]; }
     const int ls = list_start[c], le = list_start[c + 1];
     double local = 0.0;
+    int hits = 0;  // pairs inside the cutoff (the ones that pay erfc / div)
     for (int base = ls; base < le; base += TILE) {
         int nt = min(TILE, le - base);
         __syncthreads();
@@ -245,12 +246,17 @@ __global__ void __launch_bounds__(CT) coulomb_cell_kernel(const double *__restri
                 if (d < cutoff && s.idx != i) {
                     double dist = 1e-10 * d;
                     local += kmc_v_solve(dist, s.charge, sigma, k);
+                    ++hits;
                 }
             }
         }
     }
     if (active) pot[i] = local;
-    if (threadIdx.x == 0 && pair_counter) atomicAdd(pair_counter, (unsigned long long)(le - ls) * CT);
+    if (pair_counter) {
+        if (threadIdx.x == 0) atomicAdd(pair_counter, (unsigned long long)(le - ls) * CT);
+        const int wh = __reduce_add_sync(KMC_FULL_MASK, hits);
+        if ((threadIdx.x & 31) == 0 && wh) atomicAdd(pair_counter + 3, (unsigned long long)wh);
+    }
 }
 
 __global__ void sum_kernel(double *__restrict__ a, const double *__restrict__ b, int n) {
@@ -288,16 +294,27 @@ struct CoulombPlan {
     int *cell_min = nullptr, *cell_max = nullptr;  // smallest / largest site id of a cell (static)
     int *src_cstart = nullptr, *src_fill = nullptr;  // ncell+1 each (per step)
 };
-static CoulombPlan g_plan[16];  // per device
+// the plan is owned by the context (kmcb200_ctx::coulomb_plan): two contexts on one device do not share or free each
+// other's arrays, and kmcb200_destroy releases it
+static void free_plan_arrays(CoulombPlan &P) {
+    cudaFree(P.site_cell); cudaFree(P.cell_tstart); cudaFree(P.titems); cudaFree(P.blk_start); cudaFree(P.blk_cell);
+    cudaFree(P.list_start); cudaFree(P.cell_min); cudaFree(P.cell_max); cudaFree(P.src_cstart); cudaFree(P.src_fill);
+    P = CoulombPlan();
+}
+void kmc_coulomb_plan_free(kmcb200_ctx *ctx) {
+    if (!ctx->coulomb_plan) return;
+    CoulombPlan *P = (CoulombPlan *)ctx->coulomb_plan;
+    free_plan_arrays(*P);
+    delete P;
+    ctx->coulomb_plan = nullptr;
+}
 
 static int build_plan(kmcb200_ctx *ctx, CoulombPlan &P, int N, const double *x, const double *y, const double *z,
                       double cutoff, unsigned long long checksum) {
     if (P.x == x && P.N == N && P.cutoff == cutoff && P.checksum == checksum) return 0;
     if (P.site_cell) {
         KMC_CUDA(cudaStreamSynchronize(ctx->stream));
-        cudaFree(P.site_cell); cudaFree(P.cell_tstart); cudaFree(P.titems); cudaFree(P.blk_start); cudaFree(P.blk_cell);
-        cudaFree(P.list_start); cudaFree(P.cell_min); cudaFree(P.cell_max); cudaFree(P.src_cstart); cudaFree(P.src_fill);
-        P = CoulombPlan();
+        free_plan_arrays(P);
     }
     CellGridDev g;
     KMC_TRY(kmc_build_cellgrid(ctx, x, y, z, 0, N, cutoff, 0, nullptr, &g));  // scratch slots 0,1 hold start/items
@@ -349,16 +366,16 @@ extern "C" int kmcb200_poisson_gridless(kmcb200_ctx *ctx, int N, const double *x
                                         double *site_potential_charge) {
     KMC_CHECK_ARG(ctx && x && y && z && element && charge && site_potential_charge, "null pointer");
     KMC_CHECK_ARG(row_start >= 0 && row_count >= 0 && row_start + row_count <= N, "row range");
-    KMC_CHECK_ARG(ctx->device >= 0 && ctx->device < 16, "device ordinal");
     if (row_count == 0) return 0;
-    CoulombPlan &P = g_plan[ctx->device];
+    if (!ctx->coulomb_plan) ctx->coulomb_plan = new CoulombPlan();
+    CoulombPlan &P = *(CoulombPlan *)ctx->coulomb_plan;
     // 1. charged sites, ascending site order (+ coordinate checksum for the cached plan)
     int *offs = nullptr, *src_cell = nullptr, *lists = nullptr;
     Source *src = nullptr;
     unsigned long long *csum = nullptr;
     KMC_TRY(kmc_scratch(ctx, 6, (size_t)(N + 1) * sizeof(int), (void **)&offs));
     KMC_TRY(kmc_scratch(ctx, 10, 64, (void **)&csum));
-    KMC_CUDA(cudaMemsetAsync(csum, 0, 32, ctx->stream));
+    KMC_CUDA(cudaMemsetAsync(csum, 0, 32, ctx->stream));  // [0] pair tests, [1] checksum, [2] d_max, [3] pairs in range
     kmc_count_launch();
     pos_checksum_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(x, y, z, N, csum + 1);
     kmc_count_launch();
@@ -418,7 +435,7 @@ extern "C" int kmcb200_poisson_gridless(kmcb200_ctx *ctx, int N, const double *x
         KMC_CUDA(cudaGetLastError());
     }
     // 3. the pair sum
-    unsigned long long *pairs = csum;  // csum[0] was zeroed above
+    unsigned long long *pairs = csum;  // csum[0] (tests) and csum[3] (in range, via pairs_in) were zeroed above
     if (P.nblocks > 0) {
         kmc_count_launch();
         coulomb_cell_kernel<<<P.nblocks, CT, 0, ctx->stream>>>(x, y, z, src, P.blk_cell, P.blk_start, P.cell_tstart,
@@ -431,16 +448,18 @@ extern "C" int kmcb200_poisson_gridless(kmcb200_ctx *ctx, int N, const double *x
     return 0;
 }
 
-extern "C" int kmcb200_poisson_stats(kmcb200_ctx *ctx, long long *num_charged, long long *pair_tests) {
+extern "C" int kmcb200_poisson_stats(kmcb200_ctx *ctx, long long *num_charged, long long *pair_tests,
+                                     long long *pairs_in_range) {
     KMC_CHECK_ARG(ctx != nullptr, "ctx");
     if (num_charged) *num_charged = ctx->last_num_charged;
-    if (pair_tests) {
-        *pair_tests = 0;
-        if (ctx->pair_counter_dev) {
-            KMC_CUDA(cudaMemcpyAsync(ctx->h_mail, ctx->pair_counter_dev, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
-            KMC_CUDA(cudaStreamSynchronize(ctx->stream));
-            *pair_tests = (long long)*(unsigned long long *)ctx->h_mail;
-        }
+    if (pair_tests) *pair_tests = 0;
+    if (pairs_in_range) *pairs_in_range = 0;
+    if ((pair_tests || pairs_in_range) && ctx->pair_counter_dev) {
+        KMC_CUDA(cudaMemcpyAsync(ctx->h_mail, ctx->pair_counter_dev, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+        KMC_CUDA(cudaStreamSynchronize(ctx->stream));
+        const unsigned long long *h = (const unsigned long long *)ctx->h_mail;
+        if (pair_tests) *pair_tests = (long long)h[0];
+        if (pairs_in_range) *pairs_in_range = (long long)h[3];
     }
     return 0;
 }

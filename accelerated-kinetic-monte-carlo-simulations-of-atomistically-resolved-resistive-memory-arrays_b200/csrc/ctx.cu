@@ -66,6 +66,7 @@ extern "C" int kmcb200_destroy(kmcb200_ctx *ctx) {
     if (!ctx) return 0;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    kmc_coulomb_plan_free(ctx);
     for (auto &b : ctx->scratch)
         if (b.ptr) cudaFree(b.ptr);
     if (ctx->cg_state) cudaFree(ctx->cg_state);
@@ -128,6 +129,11 @@ extern "C" int kmcb200_memcpy_d2h(kmcb200_ctx *ctx, void *dst, const void *src, 
     KMC_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     return 0;
 }
+extern "C" int kmcb200_memcpy_d2d(kmcb200_ctx *ctx, void *dst, const void *src, size_t bytes) {
+    KMC_CHECK_ARG(ctx != nullptr, "ctx");
+    KMC_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    return 0;
+}
 extern "C" int kmcb200_memset(kmcb200_ctx *ctx, void *dst, int value, size_t bytes) {
     KMC_CHECK_ARG(ctx != nullptr, "ctx");
     KMC_CUDA(cudaMemsetAsync(dst, value, bytes, ctx->stream));
@@ -140,5 +146,46 @@ extern "C" int kmcb200_host_alloc_pinned(void **hptr_out, size_t bytes) {
 }
 extern "C" int kmcb200_host_free_pinned(void *hptr) {
     if (hptr) KMC_CUDA(cudaFreeHost(hptr));
+    return 0;
+}
+
+
+// ---- measurement helper: FP64 FMA peak of this device (the roofline denominator of the Coulomb sum; MEASURED_PEAKS.json
+// has no FP64 entry).  8 independent FMA chains per thread, 256 threads per CTA, 16 CTAs per SM.
+__global__ void __launch_bounds__(256) fp64_peak_kernel(int iters, double seed, double *sink) {
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-9;
+#pragma unroll 4
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    double r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (r == -1.2345) sink[0] = r;  // never true: keeps the chains alive
+}
+
+extern "C" int kmcb200_fp64_peak(kmcb200_ctx *ctx, double *tflops_host) {
+    KMC_CHECK_ARG(ctx && tflops_host, "arguments");
+    void *sink = nullptr;
+    KMC_TRY(kmc_scratch(ctx, 11, 64, &sink));
+    const int iters = 1 << 14, blocks = ctx->sm_count * 16;
+    cudaEvent_t e0, e1;
+    KMC_CUDA(cudaEventCreate(&e0));
+    KMC_CUDA(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {  // first repetition = warm-up
+        KMC_CUDA(cudaEventRecord(e0, ctx->stream));
+        kmc_count_launch();
+        fp64_peak_kernel<<<blocks, 256, 0, ctx->stream>>>(iters, 1.0 + rep, (double *)sink);
+        KMC_CUDA(cudaEventRecord(e1, ctx->stream));
+        KMC_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        KMC_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = 2.0 * 8.0 * (double)iters * 256.0 * (double)blocks;
+        if (rep > 0 && ms > 0.f && flops / (ms * 1e-3) > best) best = flops / (ms * 1e-3);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *tflops_host = best * 1e-12;
     return 0;
 }

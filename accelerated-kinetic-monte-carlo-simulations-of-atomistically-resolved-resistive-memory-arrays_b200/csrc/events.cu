@@ -338,13 +338,8 @@ __device__ __forceinline__ double mt_next_double(unsigned *mt, int &pos) {
 
 #ifdef KMC_EV_PROFILE
 #define EV_TICK(k) do { if (tid == 0) { long long now_ = clock64(); ph[k] += now_ - t_last; t_last = now_; } } while (0)
-// finer, per warp: W_START() sets the warp's reference time, W_TICK(k) adds the time since the last tick to counter k
-#define W_START() do { wt_last = clock64(); } while (0)
-#define W_TICK(k) do { __syncwarp(); long long now_ = clock64(); if (lane == 0) atomicAdd(&s_prof[k], (unsigned long long)(now_ - wt_last)); wt_last = now_; } while (0)
 #else
 #define EV_TICK(k) do { } while (0)
-#define W_START() do { } while (0)
-#define W_TICK(k) do { } while (0)
 #endif
 
 struct EvLoopArgs {
@@ -459,7 +454,6 @@ __global__ void __launch_bounds__(EV_THREADS, 1) event_loop_kernel(EvLoopArgs a)
 #ifdef KMC_EV_PROFILE
     long long ph[16] = {0};
     long long t_last = clock64();
-    long long wt_last = 0;
     __shared__ unsigned long long s_prof[16];
     if (tid < 16) s_prof[tid] = 0;
 #endif
@@ -515,7 +509,6 @@ __global__ void __launch_bounds__(EV_THREADS, 1) event_loop_kernel(EvLoopArgs a)
             const bool go = (s_event_time < a.inv_freq_threshold) && (a.max_events <= 0 || e < a.max_events);
             int ei = -1, ej = -1, ety = KMCB200_NULL_EVENT, eslot = -1;
             double Psum = 0.0, pos = 0.0, wrow = 0.0;
-            W_START();
             if (go) {
                 // ---- top level: scan_256 over the super sums (shared memory) ------------------------------
                 Scan256 sc;
@@ -529,7 +522,6 @@ __global__ void __launch_bounds__(EV_THREADS, 1) event_loop_kernel(EvLoopArgs a)
                 double number = u1 * Psum;
                 double prev, cur;
                 int ts = (Psum > 0.0) ? warp_pick_256(sc, v, number, &prev) : -1;
-                W_TICK(13);
                 int r = -1;  // all slot indices fit 32 bits: N * nn <= 16.7 M * 64 < 2^31
                 bool spec = false;
                 if (ts >= 0) {
@@ -543,7 +535,6 @@ __global__ void __launch_bounds__(EV_THREADS, 1) event_loop_kernel(EvLoopArgs a)
 #pragma unroll
                         for (int k = 0; k < 8; ++k) vv[k] = cs[KMC_CS(ts, k)];
                     });
-                    W_TICK(4);
                     if (tc >= 0) {
                         number = number - prev;
                         pos = pos + prev;
@@ -570,7 +561,6 @@ __global__ void __launch_bounds__(EV_THREADS, 1) event_loop_kernel(EvLoopArgs a)
 #pragma unroll
                             for (int k = 0; k < 8; ++k) vv[k] = (rbase + k < a.N) ? a.rowsum[rbase + k] : 0.0;
                         });
-                        W_TICK(5);
                         if (tr >= 0) {
                             number = number - prev;
                             pos = pos + prev;
@@ -613,7 +603,6 @@ __global__ void __launch_bounds__(EV_THREADS, 1) event_loop_kernel(EvLoopArgs a)
                         if (acc > number) { seln = n; break; }
                     }
                     if (seln < 0) seln = lastn;
-                    W_TICK(6);
                     if (seln >= 0) {
                         ej = __shfl_sync(KMC_FULL_MASK, (seln < 32) ? nb0 : nb1, seln & 31);
                         ety = __shfl_sync(KMC_FULL_MASK, (seln < 32) ? ty0 : ty1, seln & 31);
@@ -810,16 +799,13 @@ __global__ void __launch_bounds__(EV_THREADS, 1) event_loop_kernel(EvLoopArgs a)
             }
         } else {
             if (nc == 0) i_select = (warp == 0);  // nothing changed (no selectable event): warp 0 selects again
-            if (warp == 0) W_START();
             for (int qq = warp; qq < nc; qq += NCW) {
                 const int c = chunk_list[qq];
                 Scan256 sc;
                 const double2 *src2 = reinterpret_cast<const double2 *>(a.rowsum + c * 256 + 8 * lane);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) { double2 t2 = src2[k]; sc.a[2 * k] = t2.x; sc.a[2 * k + 1] = t2.y; }
-                if (warp == 0) { if (__any_sync(KMC_FULL_MASK, sc.a[0] == -1.2345)) s_stop = 2; W_TICK(10); }
                 warp_scan_256(sc);
-                if (warp == 0) W_TICK(11);
                 double2 *dst2 = reinterpret_cast<double2 *>(a.rowincl + c * 256 + 8 * lane);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) dst2[k] = make_double2(scan_incl(sc, 2 * k), scan_incl(sc, 2 * k + 1));
@@ -833,7 +819,6 @@ __global__ void __launch_bounds__(EV_THREADS, 1) event_loop_kernel(EvLoopArgs a)
                     left = atomicSub(&super_cnt[sidx], 1) - 1;
                 }
                 left = __shfl_sync(KMC_FULL_MASK, left, 0);
-                if (warp == 0) W_TICK(12);
                 if (left == 0) {
                     // ---- this warp finished the last dirty chunk of super sidx: re-scan the super -------------
                     __threadfence_block();

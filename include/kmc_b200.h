@@ -68,12 +68,17 @@ int kmcb200_set_stream(kmcb200_ctx *ctx, void *stream);
 int kmcb200_synchronize(kmcb200_ctx *ctx);
 int kmcb200_device_info(kmcb200_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor, size_t *total_mem);
 
+/* measurement helper: FP64 FMA peak (TFLOP/s, 2 flops per FMA) of the context's device, best of 3 timed launches:
+ * the roofline denominator of the Coulomb sum (bench.py) */
+int kmcb200_fp64_peak(kmcb200_ctx *ctx, double *tflops_host);
+
 /* Device memory helpers for hosts that do not bring their own allocator
  * (reference: hipMalloc/hipMemcpy in src/gpu_buffers.h:93-160, src/gpu_buffers.cpp:10-55). */
 int kmcb200_malloc(kmcb200_ctx *ctx, void **dptr_out, size_t bytes);
 int kmcb200_free(kmcb200_ctx *ctx, void *dptr);
 int kmcb200_memcpy_h2d(kmcb200_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes); /* async on stream */
 int kmcb200_memcpy_d2h(kmcb200_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes); /* async on stream */
+int kmcb200_memcpy_d2d(kmcb200_ctx *ctx, void *dst_dev, const void *src_dev, size_t bytes); /* async on stream */
 int kmcb200_memset(kmcb200_ctx *ctx, void *dst_dev, int value, size_t bytes);
 int kmcb200_host_alloc_pinned(void **hptr_out, size_t bytes);
 int kmcb200_host_free_pinned(void *hptr);
@@ -193,8 +198,9 @@ int kmcb200_comm_info(kmcb200_comm *comm, int *rank, int *size, unsigned *recv_m
 int kmcb200_poisson_gridless(kmcb200_ctx *ctx, int N, const double *x, const double *y, const double *z,
                              const int *element, const int *charge, double sigma, double k,
                              double cutoff_radius, int row_start, int row_count, double *site_potential_charge);
-/* number of charged sources and evaluated (i,j) pairs of the last poisson call (host sync) */
-int kmcb200_poisson_stats(kmcb200_ctx *ctx, long long *num_charged, long long *pair_tests);
+/* last poisson call (host sync): number of charged sources, (i,j) distance tests, pairs inside the cutoff (the ones
+ * that evaluate erfc / division).  Any pointer may be NULL. */
+int kmcb200_poisson_stats(kmcb200_ctx *ctx, long long *num_charged, long long *pair_tests, long long *pairs_in_range);
 
 /* a9.  Replaces the kernel of sum_and_gather_potential (src/gpu_solvers.h:181,
  * src/potential_solver_gpu.cu:832-843,1130-1151): site_potential_charge += site_potential_boundary. */

@@ -742,6 +742,30 @@ void orc_build_events(int N, int nn, const int *neigh, const int *layer, double 
     }
 }
 
+// Device::makeSubstoichiometric (Device.cpp:180-211): n_add = int(concentration * #O); draw loc = int(u * N_atom) from
+// mt19937(seed) until n_add oxygen ATOMS (sites that are neither d nor Od, in site order) have become vacancies.
+int orc_make_substoichiometric(int N, int *element, double vacancy_concentration, unsigned rnd_seed) {
+    std::vector<int> atom_ind;
+    int num_O = 0;
+    for (int i = 0; i < N; ++i) {
+        if (element[i] == ORC_O) num_O++;
+        if (element[i] != ORC_DEFECT && element[i] != ORC_OXYGEN_DEFECT) atom_ind.push_back(i);  // Device.cpp:116-143
+    }
+    const int N_atom = (int)atom_ind.size();
+    int num_V_add = (int)(vacancy_concentration * num_O);
+    const int added = num_V_add;
+    Rng rng(rnd_seed);
+    while (num_V_add > 0) {
+        double random_num = rng.next();
+        int loc = (int)(random_num * N_atom);
+        if (element[atom_ind[loc]] == ORC_O) {
+            element[atom_ind[loc]] = ORC_VACANCY;
+            num_V_add--;
+        }
+    }
+    return added;
+}
+
 void *orc_rng_create(unsigned seed) { return new Rng(seed); }
 void orc_rng_destroy(void *rng) { delete (Rng *)rng; }
 double orc_rng_next(void *rng) { return ((Rng *)rng)->next(); }

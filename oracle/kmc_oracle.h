@@ -111,6 +111,9 @@ void orc_build_events(int N, int nn, const int *neigh, const int *layer, double 
                       const double *E_Odiff, int row_start, int row_count, int *type_out,
                       double *prob_out);
 
+/* ---- host model: Device::makeSubstoichiometric (Device.cpp:180-211); returns the number of vacancies created */
+int orc_make_substoichiometric(int N, int *element, double vacancy_concentration, unsigned rnd_seed);
+
 /* ---- a11: RNG (random_num.h:4-26; libstdc++ mt19937 + uniform_real_distribution) - */
 void *orc_rng_create(unsigned seed);
 void orc_rng_destroy(void *rng);
