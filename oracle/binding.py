@@ -41,7 +41,8 @@ class OrcStepInfo(C.Structure):
 
 def build(force: bool = False):
     """compile the oracle (and oracle/_ref when /root/reference exists) with oracle/Makefile"""
-    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(os.path.join(HERE, "kmc_oracle.cpp")):
+    srcs = [os.path.join(HERE, f) for f in ("kmc_oracle.cpp", "kirchhoff_oracle.cpp", "kmc_oracle.h")]
+    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(f) for f in srcs):
         subprocess.run(["make", "-s", "-C", HERE, os.path.join(HERE, "_build", "libkmc_oracle.so")], check=True)
     if os.path.isdir("/root/reference/src") and (force or not os.path.exists(REF_LIB)):
         subprocess.run(["make", "-s", "-C", HERE, "ref"], check=True)
@@ -325,3 +326,147 @@ def ref_poisson_gridless_rows(x, y, z, charge, lattice, pbc, sigma, k, row_begin
     L.ref_poisson_gridless_rows(C.c_int(len(x)), _p(x), _p(y), _p(z), _p(charge), _p(lat), C.c_int(int(pbc)),
                                 C.c_double(sigma), C.c_double(k), C.c_int(row_begin), C.c_int(row_end), _p(out))
     return out
+
+
+# ---- Kirchhoff / current chain (oracle/kirchhoff_oracle.cpp) ---------------------------------------
+M_0 = 9.11e-31   # src/input_parser.h (electron rest mass used by the reference)
+
+
+def atoms_compact(element):
+    element = _i(element)
+    out = np.zeros(len(element), dtype=np.int32)
+    n = lib().orc_atoms_compact(C.c_int(len(element)), _p(element), _p(out))
+    return out[:n].copy()
+
+
+def T_sparsity(ax, ay, az, nn_dist, num_source_inj, num_ground_ext, row_start=0, row_count=None):
+    ax, ay, az = _d(ax), _d(ay), _d(az)
+    N_atom = len(ax)
+    row_count = N_atom + 1 - row_start if row_count is None else row_count
+    L = lib(); L.orc_T_sparsity.restype = C.c_long
+    rp = np.zeros(row_count + 1, dtype=np.int32)
+    args = [C.c_int(N_atom), _p(ax), _p(ay), _p(az), C.c_double(nn_dist), C.c_int(num_source_inj), C.c_int(num_ground_ext),
+            C.c_int(row_start), C.c_int(row_count)]
+    nnz = L.orc_T_sparsity(*args, _p(rp), None)
+    col = np.zeros(max(nnz, 1), dtype=np.int32)
+    L.orc_T_sparsity(*args, _p(rp), _p(col))
+    return rp, col[:nnz]
+
+
+def T_values(ax, ay, az, a_element, a_charge, metals, nn_dist, high_G, low_G, loop_G, num_source_inj, num_ground_ext,
+             row_ptr, col, row_start=0):
+    ax, ay, az, a_element, a_charge, metals = _d(ax), _d(ay), _d(az), _i(a_element), _i(a_charge), _i(metals)
+    rows = len(row_ptr) - 1
+    data = np.zeros(max(len(col), 1)); diag = np.zeros(rows)
+    lib().orc_T_values(C.c_int(len(ax)), _p(ax), _p(ay), _p(az), _p(a_element), _p(a_charge), _p(metals),
+                       C.c_int(len(metals)), C.c_double(nn_dist), C.c_double(high_G), C.c_double(low_G), C.c_double(loop_G),
+                       C.c_int(num_source_inj), C.c_int(num_ground_ext), C.c_int(row_start), C.c_int(rows),
+                       _p(_i(row_ptr)), _p(_i(col)), _p(data), _p(diag))
+    return data[:len(col)], diag
+
+
+def tunnel_points(a_element, ax):
+    a_element, ax = _i(a_element), _d(ax)
+    out = np.zeros(len(ax), dtype=np.int32)
+    n = lib().orc_tunnel_points(C.c_int(len(ax)), _p(a_element), _p(ax), _p(out))
+    if n < 0:
+        raise ValueError("atom 0 qualifies as a tunnel point (the reference cannot list it)")
+    return out[:n].copy()
+
+
+def tunnel_block(ax, ay, az, a_element, a_cb, metals, nn_dist, num_layers_contact, num_source_inj, num_ground_ext, m_e, V0,
+                 tunnel_atoms, t_start=0, t_count=None):
+    ax, ay, az, a_element, a_cb, metals, tunnel_atoms = _d(ax), _d(ay), _d(az), _i(a_element), _d(a_cb), _i(metals), _i(tunnel_atoms)
+    nt = len(tunnel_atoms)
+    t_count = nt - t_start if t_count is None else t_count
+    L = lib(); L.orc_tunnel_block.restype = C.c_long
+    rp = np.zeros(t_count + 1, dtype=np.int32)
+    args = [C.c_int(len(ax)), _p(ax), _p(ay), _p(az), _p(a_element), _p(a_cb), _p(metals), C.c_int(len(metals)),
+            C.c_double(nn_dist), C.c_int(num_layers_contact), C.c_int(num_source_inj), C.c_int(num_ground_ext),
+            C.c_double(m_e), C.c_double(V0), C.c_int(nt), _p(tunnel_atoms), C.c_int(t_start), C.c_int(t_count)]
+    nnz = L.orc_tunnel_block(*args, _p(rp), None, None, None)
+    col = np.zeros(max(nnz, 1), dtype=np.int32); data = np.zeros(max(nnz, 1)); diag = np.zeros(max(t_count, 1))
+    L.orc_tunnel_block(*args, _p(rp), _p(col), _p(data), _p(diag))
+    return rp, col[:nnz], data[:nnz], diag[:t_count]
+
+
+def split_spmv(row_ptr, col, data, t_row_ptr, t_col, t_data, tunnel_rows, x, lanes=8):
+    n = len(row_ptr) - 1
+    y = np.zeros(n)
+    lib().orc_split_spmv(C.c_int(n), _p(_i(row_ptr)), _p(_i(col)), _p(_d(data)), C.c_int(len(tunnel_rows)), _p(_i(t_row_ptr)),
+                         _p(_i(t_col)), _p(_d(t_data)), _p(_i(tunnel_rows)), _p(_d(x)), _p(y), C.c_int(lanes))
+    return y
+
+
+def pcg_jacobi_split_sparse(row_ptr, col, data, t_row_ptr, t_col, t_data, tunnel_rows, inv_diag, rhs, x0, tol, max_it=100,
+                            lanes=8):
+    n = len(row_ptr) - 1
+    r = _d(rhs).copy(); x = _d(x0).copy(); stats = np.zeros(2)
+    it = lib().orc_pcg_jacobi_split_sparse(C.c_int(n), _p(_i(row_ptr)), _p(_i(col)), _p(_d(data)), C.c_int(len(tunnel_rows)),
+                                           _p(_i(t_row_ptr)), _p(_i(t_col)), _p(_d(t_data)), _p(_i(tunnel_rows)),
+                                           _p(_d(inv_diag)), _p(r), _p(x), C.c_double(tol), C.c_int(max_it), C.c_int(lanes),
+                                           _p(stats))
+    return x, r, it, stats
+
+
+def imacro(row_ptr, col, data, virtual_potentials, G0):
+    L = lib(); L.orc_imacro.restype = C.c_double
+    return L.orc_imacro(_p(_i(row_ptr)), _p(_i(col)), _p(_d(data)), _p(_d(virtual_potentials)), C.c_double(G0))
+
+
+def update_CB_edge(s, sp, site_cb0=None, max_it=50000, high_G=None, low_G=None, Vd=None):
+    """update_CB_edge_gpu_sparse on structure s with K sparsity sp; returns (site_CB_edge [J], CG iterations)"""
+    cb = np.zeros(s.N) if site_cb0 is None else _d(site_cb0).copy()
+    el, metals = _i(s.element), _i(s.metals)
+    it = lib().orc_update_CB_edge(C.c_int(s.N), C.c_int(s.N_left), C.c_int(s.N_right), _p(el), _p(metals), C.c_int(len(metals)),
+                                  _p(sp["row_ptr"]), _p(sp["col"]), _p(sp["left_row_ptr"]), _p(sp["left_col"]),
+                                  _p(sp["right_row_ptr"]), _p(sp["right_col"]), C.c_double(s.Vd if Vd is None else Vd),
+                                  C.c_double(s.high_G if high_G is None else high_G),
+                                  C.c_double(s.low_G if low_G is None else low_G), _p(cb), C.c_int(max_it), C.c_int(8))
+    return cb, it
+
+
+class KirchhoffOracle:
+    """The reference's sparse_dist current solver on one rank, driven by the oracle:
+    setLaplacePotential (src/kmc_main.cpp:272) -> initialize_sparsity_T (:273) -> update_power_gpu_sparse_dist (:467)
+    with the constants of src/kmc_main.cpp:294-301."""
+
+    def __init__(self, s, sp, num_layers_contact, m_r=0.85, V0=1.6, site_charge=None, site_cb=None, cb_max_it=50000):
+        self.s = s
+        self.loop_G, self.high_G, self.low_G = s.high_G * 10000000, s.high_G * 100000, s.low_G   # kmc_main.cpp:294-296
+        self.G0 = 2 * 3.8612e-5 * 1e-5                                                              # :297-298
+        self.nsi = self.nge = s.N_left                                                              # :300-301
+        self.nlc, self.m_e, self.V0 = num_layers_contact, m_r * M_0, V0
+        self.site_cb, self.cb_iterations = (update_CB_edge(s, sp, max_it=cb_max_it) if site_cb is None else (site_cb, 0))
+        self.atom_ind = atoms_compact(s.element)
+        a = self.atom_ind
+        self.ax, self.ay, self.az = _d(s.x[a]), _d(s.y[a]), _d(s.z[a])
+        self.N_atom = len(a)
+        self.row_ptr, self.col = T_sparsity(self.ax, self.ay, self.az, s.nn_dist, self.nsi, self.nge)
+        self.x = np.zeros(self.N_atom + 1)      # gpubuf.atom_virtual_potentials (warm start of the next solve)
+        self.assemble(s.element, np.zeros(s.N, np.int32) if site_charge is None else site_charge)
+
+    def assemble(self, site_element, site_charge):
+        s, a = self.s, self.atom_ind
+        self.a_el, self.a_ch, self.a_cb = _i(np.asarray(site_element)[a]), _i(np.asarray(site_charge)[a]), _d(self.site_cb[a])
+        self.data, self.diag = T_values(self.ax, self.ay, self.az, self.a_el, self.a_ch, s.metals, s.nn_dist, self.high_G,
+                                        self.low_G, self.loop_G, self.nsi, self.nge, self.row_ptr, self.col)
+        self.tunnel_atoms = tunnel_points(self.a_el, self.ax)
+        metals2 = list(s.metals)[:2]                                        # num_metals = 2 hard-coded (init...T.cu:800)
+        self.t_row_ptr, self.t_col, self.t_data, self.t_diag = tunnel_block(
+            self.ax, self.ay, self.az, self.a_el, self.a_cb, metals2, s.nn_dist, self.nlc, self.nsi, self.nge, self.m_e,
+            self.V0, self.tunnel_atoms)
+        self.tunnel_rows = (self.tunnel_atoms + 2).astype(np.int32)
+        d = self.diag.copy()
+        d[self.tunnel_rows] += self.t_diag                                   # assemble_preconditioner
+        self.inv_diag = 1.0 / d                                              # invert_diag
+        self.rhs = np.zeros(self.N_atom + 1)
+        self.rhs[0], self.rhs[1] = -self.loop_G * s.Vd, self.loop_G * s.Vd   # current_solver_gpu.cu:1626-1631
+
+    def solve(self, max_it=100):
+        tol = 1e-30 * self.N_atom                                            # current_solver_gpu.cu:1455
+        self.x, r, it, stats = pcg_jacobi_split_sparse(self.row_ptr, self.col, self.data, self.t_row_ptr, self.t_col,
+                                                       self.t_data, self.tunnel_rows, self.inv_diag, self.rhs, self.x, tol,
+                                                       max_it)
+        self.imacro = imacro(self.row_ptr, self.col, self.data, self.x, self.G0)
+        return it
