@@ -130,6 +130,16 @@ SIGNATURES = {
     "kmcb200_build_event_list": (_i, [_vp, _vp, _i, _i, _vp, _vp, _d, _d, _d, _d, _vp, _vp, _vp, _vp, _vp, _vp]),
     "kmcb200_events_pointers": (_i, [_vp, _pvp, _pvp]),
     "kmcb200_events_log": (_i, [_vp, _i, _pi, _pd, _pi]),
+    "kmcb200_update_CB_edge": (_i, [_vp, _vp, _i, _i, _i, _vp, _pi, _i, _d, _d, _d, _vp, _i, _pi]),
+    "kmcb200_initialize_sparsity_T": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _d, _i, _i, _i, _pvp]),
+    "kmcb200_tmat_destroy": (_i, [_vp]),
+    "kmcb200_tmat_info": (_i, [_vp, _pi, _pll, _pi, _pll]),
+    "kmcb200_tmat_pointers": (_i, [_vp] + [_pvp] * 11),
+    "kmcb200_assemble_T": (_i, [_vp, _vp, _vp, _vp, _vp, _pi, _i, _d, _d, _d, _d, _d, _d]),
+    "kmcb200_tmat_spmv": (_i, [_vp, _vp, _vp, _vp]),
+    "kmcb200_pcg_jacobi_split_sparse": (_i, [_vp, _vp, _vp, _vp, _d, _i, _pi]),
+    "kmcb200_imacro": (_i, [_vp, _vp, _vp, _d, _pd]),
+    "kmcb200_update_power_sparse": (_i, [_vp, _vp, _vp, _vp, _vp, _pi, _i, _d, _d, _d, _d, _d, _d, _d, _vp, _pd, _pi]),
     "kmcb200_parse_parameters": (_i, [C.c_char_p, C.POINTER(Params)]),
     "kmcb200_parse_parameter_vector": (_i, [C.c_char_p, _i, _i, _pd]),
     "kmcb200_xyz_count": (_i, [C.c_char_p]),
@@ -427,12 +437,105 @@ class Context:
     def sum_potential(self, pot_charge, pot_boundary):
         _check(self.lib.kmcb200_sum_potential(self.h, pot_charge.numel(), _ptr(pot_charge), _ptr(pot_boundary)))
 
+    # -- a12: Kirchhoff / current chain
+    def update_CB_edge(self, K, N, N_left, N_right, element, metals, Vd, high_G, low_G, site_cb, max_it=50000) -> int:
+        m = (C.c_int * max(len(metals), 1))(*[int(v) for v in metals])
+        it = C.c_int(0)
+        _check(self.lib.kmcb200_update_CB_edge(self.h, K.h, N, N_left, N_right, _ptr(element), m, len(metals), Vd, high_G,
+                                               low_G, _ptr(site_cb), max_it, C.byref(it)))
+        return it.value
+
+    def initialize_sparsity_T(self, element, x, y, z, nn_dist, num_source_inj, num_ground_ext, num_layers_contact):
+        h = C.c_void_p()
+        _check(self.lib.kmcb200_initialize_sparsity_T(self.h, element.numel(), _ptr(element), _ptr(x), _ptr(y), _ptr(z),
+                                                      nn_dist, num_source_inj, num_ground_ext, num_layers_contact,
+                                                      C.byref(h)))
+        return TMatrix(self, h)
+
+    def assemble_T(self, T, element, charge, site_cb, metals, Vd, high_G, low_G, loop_G, m_e, V0):
+        m = (C.c_int * max(len(metals), 1))(*[int(v) for v in metals])
+        _check(self.lib.kmcb200_assemble_T(self.h, T.h, _ptr(element), _ptr(charge), _ptr(site_cb), m, len(metals), Vd,
+                                           high_G, low_G, loop_G, m_e, V0))
+        T.refresh()
+
+    def tmat_spmv(self, T, x, y):
+        _check(self.lib.kmcb200_tmat_spmv(self.h, T.h, _ptr(x), _ptr(y)))
+
+    def pcg_jacobi_split_sparse(self, T, r, x, tol, max_it=100) -> int:
+        it = C.c_int(0)
+        _check(self.lib.kmcb200_pcg_jacobi_split_sparse(self.h, T.h, _ptr(r), _ptr(x), tol, max_it, C.byref(it)))
+        return it.value
+
+    def imacro(self, T, V, G0) -> float:
+        out = C.c_double(0)
+        _check(self.lib.kmcb200_imacro(self.h, T.h, _ptr(V), G0, C.byref(out)))
+        return out.value
+
+    def update_power_sparse(self, T, element, charge, site_cb, metals, Vd, high_G, low_G, loop_G, G0, m_e, V0, V):
+        """-> (I_macro, PCG iterations); V = atom_virtual_potentials (N_atom + 1), warm start in / solution out"""
+        m = (C.c_int * max(len(metals), 1))(*[int(v) for v in metals])
+        im, it = C.c_double(0), C.c_int(0)
+        _check(self.lib.kmcb200_update_power_sparse(self.h, T.h, _ptr(element), _ptr(charge), _ptr(site_cb), m, len(metals),
+                                                    Vd, high_G, low_G, loop_G, G0, m_e, V0, _ptr(V), C.byref(im),
+                                                    C.byref(it)))
+        T.refresh()
+        return im.value, it.value
+
     # -- a10
     def events_create(self, neigh):
         N, nn = neigh.shape
         h = C.c_void_p()
         _check(self.lib.kmcb200_events_create(self.h, N, nn, _ptr(neigh), C.byref(h)))
         return Events(self, h, N, nn)
+
+
+M_0 = 9.11e-31   # electron rest mass the reference uses (src/input_parser.h:99)
+
+
+class TMatrix:
+    """kmcb200_tmat handle: the Kirchhoff system (reference GPUBuffers::T_distributed + tunnel sub-block + atom arrays)."""
+
+    def __init__(self, ctx: "Context", h):
+        self.ctx, self.h = ctx, h
+        self.refresh()
+
+    def refresh(self):
+        a, b, c, d = C.c_int(0), C.c_longlong(0), C.c_int(0), C.c_longlong(0)
+        _check(self.ctx.lib.kmcb200_tmat_info(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        self.N_atom, self.nnz, self.n_tunnel, self.tunnel_nnz = a.value, b.value, c.value, d.value
+
+    def _d2h(self, ptr, n, dtype):
+        out = np.zeros(max(int(n), 1), dtype=dtype)
+        if n > 0:
+            _check(self.ctx.lib.kmcb200_memcpy_d2h(self.ctx.h, out.ctypes.data_as(C.c_void_p), C.c_void_p(ptr), int(n) * out.itemsize))
+            self.ctx.sync()
+        return out[:int(n)]
+
+    def to_host(self):
+        self.refresh()
+        ps = [C.c_void_p() for _ in range(11)]
+        _check(self.ctx.lib.kmcb200_tmat_pointers(self.h, *[C.byref(p) for p in ps]))
+        v = [p.value for p in ps]
+        n, nt = self.N_atom + 1, self.n_tunnel
+        out = {"atom_ind": self._d2h(v[0], self.N_atom, np.int32), "row_ptr": self._d2h(v[1], n + 1, np.int32),
+               "col": self._d2h(v[2], self.nnz, np.int32), "val": self._d2h(v[3], self.nnz, np.float64),
+               "inv_diag": self._d2h(v[4], n, np.float64), "rhs": self._d2h(v[5], n, np.float64),
+               "tunnel_atoms": self._d2h(v[6], nt, np.int32), "t_row_ptr": self._d2h(v[7], nt + 1 if nt else 0, np.int32)}
+        if nt:
+            out.update({"t_col": self._d2h(v[8], self.tunnel_nnz, np.int32), "t_val": self._d2h(v[9], self.tunnel_nnz, np.float64),
+                        "t_diag": self._d2h(v[10], nt, np.float64)})
+        return out
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.kmcb200_tmat_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class KMatrix:

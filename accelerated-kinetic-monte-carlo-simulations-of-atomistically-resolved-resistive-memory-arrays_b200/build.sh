@@ -8,7 +8,7 @@ FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 --fmad=false -std=c
 mkdir -p "$HERE/build"
 objs=""
 pids=""
-for f in ctx scan lists kmat spmv_plan pcg coulomb events comm; do
+for f in ctx scan lists kmat spmv_plan pcg coulomb events comm kirchhoff; do
   src="$HERE/csrc/$f.cu"
   [ -f "$src" ] || continue
   obj="$HERE/build/$f.o"

@@ -100,6 +100,34 @@ __device__ __forceinline__ double kmc_v_solve(double r_dist, int charge, double 
     const double q = 1.60217663e-19;
     return (double)charge * erfc(r_dist / (sigma * sqrt(2.0))) * k * q / r_dist;
 }
+// Deterministic exp / x^1.5 for the WKB tunnel coefficients (initialize_sparsity_T.cu:497-614).  The reference calls the
+// device math library there; libm implementations differ in the last ulp, and the macroscopic current is a strongly
+// cancelling sum of the resulting potentials, so a 1-ulp difference in a coefficient shows up at 1e-9 relative in I_macro.
+// These two routines use only +, *, fma, sqrt, ldexp (all correctly rounded on both sides), are restated operation by
+// operation in the CPU oracle, and agree with libm's exp / pow(x, 1.5) to <= 2 ulp.
+__device__ __forceinline__ double kmc_det_exp(double x) {
+    if (!(x > -745.2)) return 0.0;
+    if (x > 709.7) return 1.0 / 0.0;
+    const double k = nearbyint(x * 1.4426950408889634);           // round(x / ln 2)
+    double r = fma(-k, 0.693147180369123816490e+00, x);            // ln2_hi
+    r = fma(-k, 1.90821492927058770002e-10, r);                    // ln2_lo
+    double p = 1.0 / 6227020800.0;                                 // Taylor, degree 13, Horner with fma (|r| <= 0.347)
+    p = fma(p, r, 1.0 / 479001600.0);
+    p = fma(p, r, 1.0 / 39916800.0);
+    p = fma(p, r, 1.0 / 3628800.0);
+    p = fma(p, r, 1.0 / 362880.0);
+    p = fma(p, r, 1.0 / 40320.0);
+    p = fma(p, r, 1.0 / 5040.0);
+    p = fma(p, r, 1.0 / 720.0);
+    p = fma(p, r, 1.0 / 120.0);
+    p = fma(p, r, 1.0 / 24.0);
+    p = fma(p, r, 1.0 / 6.0);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    return ldexp(p, (int)k);
+}
+__device__ __forceinline__ double kmc_det_pow15(double x) { return x * sqrt(x); }
 __device__ __forceinline__ bool kmc_possibly_charged(int el) {
     return el == KMCB200_OXYGEN_DEFECT || el == KMCB200_O || el == KMCB200_VACANCY || el == KMCB200_DEFECT;
 }

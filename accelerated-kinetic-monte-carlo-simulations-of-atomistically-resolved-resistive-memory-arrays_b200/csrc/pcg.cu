@@ -10,6 +10,7 @@
 
 #include "comm.cuh"
 #include "kmat.cuh"
+#include "pcg.cuh"
 
 struct CgState {
     double bb, rz, rz_old, pAp, tol2, scalar_out;
@@ -388,6 +389,65 @@ __global__ void __launch_bounds__(CH) cg_update_kernel(int rows, int nchunks, co
     }
 }
 
+// ---- split-sparse extension (reference dist_iterative/dist_spmv_split_sparse.cpp:5-79, spmm_split_sparse1):
+// Ap += scatter(T_tunnel * gather(p)).  One warp per local tunnel row; row reduction spec with 32 lanes (lane l takes
+// entries l, l+32, ... with fma in increasing k, then the xor butterfly 16..1); the gather reads p through the
+// global-indexed p vector, so no packed copy of the tunnel entries is needed.
+__global__ void __launch_bounds__(256) tunnel_spmv_kernel(TunnelDev t, const double *__restrict__ pg, double *__restrict__ Ap,
+                                                         const CgState *__restrict__ st, int check_done) {
+    if (check_done && st->done) return;
+    const int lane = threadIdx.x & 31;
+    const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= t.n_local) return;
+    const int s = t.row_ptr[r], e = t.row_ptr[r + 1];
+    double acc = 0.0;
+    for (int k0 = s + lane; k0 < e; k0 += 128) {  // 4 (val, col, x) triples in flight per lane; FMA order unchanged
+        double v[4], xv[4];
+        int c[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int k = k0 + 32 * u;
+            const bool ok = k < e;
+            v[u] = ok ? __ldcs(t.val + k) : 0.0;
+            c[u] = ok ? __ldcs(t.col + k) : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) xv[u] = (c[u] >= 0) ? __ldg(pg + __ldg(t.rows_global + c[u])) : 0.0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (c[u] >= 0) acc = fma(v[u], xv[u], acc);
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) acc = acc + __shfl_xor_sync(KMC_FULL_MASK, acc, off);
+    if (lane == 0) {
+        const int lr = t.rows_local[r];
+        Ap[lr] = Ap[lr] + acc;  // unpack_add (utils_cg.cu)
+    }
+}
+
+// p.Ap when the SpMV could not fuse it (the tunnel part is added by a second kernel)
+template <bool FUSE>
+__global__ void __launch_bounds__(CH) cg_pap_kernel(int rows, int nchunks, const double *__restrict__ p_full,
+                                                   const double *__restrict__ Ap, CommDev cm, unsigned long long dot_seq,
+                                                   CgState *__restrict__ st) {
+    if (st->done) return;
+    __shared__ double red[8];
+    __shared__ int flag;
+    for (int c = blockIdx.x; c < nchunks; c += gridDim.x) {
+        const int i = c * CH + threadIdx.x;
+        double v = 0.0;
+        if (i < rows) v = p_full[cm.row_start + i] * Ap[i];
+        const double cv = kmc_chunk_reduce_256(v, red);
+        if (threadIdx.x == 0) publish_partial(cm, 0, c, cv);
+    }
+    if (FUSE) {
+        if (last_cta(&st->cnt[5], &flag, false)) {
+            finish_pap(cm, nchunks, dot_seq, st, red);
+            if (threadIdx.x == 0) st->cnt[5] = 0;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(CH) dot_kernel(long long n, const double *__restrict__ u, const double *__restrict__ v,
                                                 double *__restrict__ partials, CgState *__restrict__ st) {
     __shared__ double red[8];
@@ -540,12 +600,38 @@ extern "C" int kmcb200_dot(kmcb200_ctx *ctx, const double *u, const double *v, l
     return 0;
 }
 
+static int tunnel_launch(kmcb200_ctx *ctx, const TunnelDev &t, const double *pg, double *Ap, int check_done) {
+    if (t.n_local <= 0) return 0;
+    kmc_count_launch();
+    tunnel_spmv_kernel<<<(unsigned)((t.n_local + 7) / 8), 256, 0, ctx->stream>>>(t, pg, Ap, ctx->cg_state, check_done);
+    KMC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// y = T_neighbor x + scatter(T_tunnel gather(x)) on one rank (spmm_split_sparse1)
+int kmc_split_spmv(kmcb200_ctx *ctx, kmcb200_kmat *K, const TunnelDev *tun, const double *x_local, double *y_local) {
+    KMC_CHECK_ARG(K->comm != nullptr && K->comm->size == 1, "split-sparse SpMV: single-rank call");
+    KMC_TRY(ensure_cg_workspace(ctx, 1));
+    KMC_TRY(spmv_launch(ctx, K, x_local, y_local, false, 0, 0));
+    if (tun) KMC_TRY(tunnel_launch(ctx, *tun, x_local, y_local, 0));
+    return 0;
+}
+
 extern "C" int kmcb200_pcg_jacobi(kmcb200_ctx *ctx, kmcb200_kmat *K, double *r_local, double *x_local,
                                   const double *diag_inv_local, double relative_tolerance, int max_iterations,
                                   int *iterations_host) {
+    return kmc_pcg_run(ctx, K, nullptr, r_local, x_local, diag_inv_local, relative_tolerance, max_iterations,
+                       iterations_host);
+}
+
+// Jacobi-PCG; tun != NULL: the operator is T_neighbor + tunnel sub-block (conjugate_gradient_jacobi_split_sparse,
+// dist_iterative/dist_conjugate_gradient_split_sparse.cpp:18-166), same update order.
+int kmc_pcg_run(kmcb200_ctx *ctx, kmcb200_kmat *K, const TunnelDev *tun, double *r_local, double *x_local,
+                const double *diag_inv_local, double relative_tolerance, int max_iterations, int *iterations_host) {
     KMC_CHECK_ARG(ctx && K && r_local && x_local && diag_inv_local, "null pointer");
     KMC_CHECK_ARG(K->comm != nullptr, "kmat has no exchange plan");
     kmcb200_comm *C = K->comm;
+    KMC_CHECK_ARG(tun == nullptr || C->size == 1, "split-sparse PCG with a tunnel block: single-rank call");
     if (C->size > 1 && !C->peers_open) {
         kmc_set_error("row-sharded PCG: kmcb200_comm_open_peers / kmcb200_comm_set_send_masks were not called");
         return KMCB200_E_COMM;
@@ -567,6 +653,7 @@ extern "C" int kmcb200_pcg_jacobi(kmcb200_ctx *ctx, kmcb200_kmat *K, double *r_l
     unsigned long long hs = 0;
     if (C->size == 1) {
         KMC_TRY(spmv_launch(ctx, K, x_local, K->Ap, false, 1, 0));
+        if (tun) KMC_TRY(tunnel_launch(ctx, *tun, x_local, K->Ap, 0));
         hs = C->halo_seq;
         buf = (int)(hs & 1);
     } else {
@@ -619,9 +706,17 @@ extern "C" int kmcb200_pcg_jacobi(kmcb200_ctx *ctx, kmcb200_kmat *K, double *r_l
             cg_pupdate_kernel<1><<<eb, CH, 0, ctx->stream>>>(rows, (int)nchunks, K->z, C->dev.p_full[nb ^ 1], C->dev.p_full[nb],
                                                             C->dev, nb, hs2, st);
             if (rec) cudaEventRecord(pe[1], ctx->stream);
-            {
+            if (!tun) {
                 const unsigned long long ds = ++C->dot_seq;
                 KMC_TRY(spmv_launch(ctx, K, C->dev.p_full[nb], K->Ap, true, fuse, ds));
+                if (!fuse) { kmc_count_launch(); dot_finalize_kernel<<<1, CH, 0, ctx->stream>>>(C->dev, 0, (int)nchunks, ds, st); }
+            } else {  // neighbour part, tunnel part, then p.Ap over the sum
+                const unsigned long long ds = ++C->dot_seq;
+                KMC_TRY(spmv_launch(ctx, K, C->dev.p_full[nb], K->Ap, false, 0, 0));
+                KMC_TRY(tunnel_launch(ctx, *tun, C->dev.p_full[nb], K->Ap, 1));
+                kmc_count_launch();
+                if (fuse) cg_pap_kernel<true><<<eb, CH, 0, ctx->stream>>>(rows, (int)nchunks, C->dev.p_full[nb], K->Ap, C->dev, ds, st);
+                else cg_pap_kernel<false><<<eb, CH, 0, ctx->stream>>>(rows, (int)nchunks, C->dev.p_full[nb], K->Ap, C->dev, ds, st);
                 if (!fuse) { kmc_count_launch(); dot_finalize_kernel<<<1, CH, 0, ctx->stream>>>(C->dev, 0, (int)nchunks, ds, st); }
             }
             if (rec) cudaEventRecord(pe[2], ctx->stream);

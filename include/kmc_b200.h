@@ -241,6 +241,57 @@ int kmcb200_events_pointers(kmcb200_events *ev, double **event_prob, unsigned ch
 int kmcb200_events_log(kmcb200_events *ev, int max_rows, int *log_host, double *psum_host, int *rows_host);
 
 /* ------------------------------------------------------------------------------------------------
+ * a12.  Kirchhoff / current chain (single rank).  The reference's driver of this chain is a timing harness that
+ * exit(1)s (src/current_solver_gpu.cu:1449-1801) behind a guard that is never true in its shipped main
+ * (src/KMC_comm.h:243); these calls are the chain itself.
+ *
+ * kmcb200_update_CB_edge replaces update_CB_edge_gpu_sparse (src/gpu_solvers.h:143-146,
+ * src/potential_solver_gpu.cu:673-772): Laplace-type solve on the K sparsity for the conduction-band edge of every site
+ * [J]; contacts fixed to +-Vd/2.  site_CB_edge: N doubles (interior: initial guess in).  K: the 1-rank K sparsity.
+ * max_iterations bounds the CG loop of solve_sparse_CG_Jacobi (the reference only warns after 50000). */
+typedef struct kmcb200_tmat kmcb200_tmat; /* T_distributed + tunnel sub-block + atom arrays (src/gpu_buffers.h) */
+int kmcb200_update_CB_edge(kmcb200_ctx *ctx, kmcb200_kmat *kmat, int N, int N_left, int N_right, const int *element,
+                           const int *metals_host, int num_metals, double Vd, double high_G, double low_G,
+                           double *site_CB_edge, int max_iterations, int *iterations_host);
+/* Replaces initialize_sparsity_T (src/gpu_solvers.h:57, src/initialize_sparsity_T.cu:948-1153): compacts the atoms
+ * (sites that are neither DEFECT nor OXYGEN_DEFECT) and builds the CSR of T_neighbor over N_atom + 1 nodes
+ * (0 = extraction, 1 = injection, i >= 2 = atom i - 2; the last atom is the ground node, cut from the graph). */
+int kmcb200_initialize_sparsity_T(kmcb200_ctx *ctx, int N, const int *site_element, const double *x, const double *y,
+                                  const double *z, double nn_dist, int num_source_inj, int num_ground_ext,
+                                  int num_layers_contact, kmcb200_tmat **tmat_out);
+int kmcb200_tmat_destroy(kmcb200_tmat *tmat);
+int kmcb200_tmat_info(kmcb200_tmat *tmat, int *N_atom, long long *nnz, int *n_tunnel, long long *tunnel_nnz);
+/* device pointers owned by tmat (any may be NULL): atom -> site index, T_neighbor CSR, Jacobi M^-1, rhs, tunnel points
+ * (atom indices), tunnel CSR (columns = tunnel-point ids), tunnel diagonal */
+int kmcb200_tmat_pointers(kmcb200_tmat *tmat, int **atom_ind, int **row_ptr, int **col, double **val, double **inv_diag,
+                          double **rhs, int **tunnel_atoms, int **t_row_ptr, int **t_col, double **t_val,
+                          double **t_diag);
+/* Assembly part of update_power_gpu_sparse_dist (src/gpu_solvers.h:212-218, src/current_solver_gpu.cu:1494-1633):
+ * update_atom_arrays, populate_T_dist, update_diagonal_sparse, assemble_sparse_T_submatrix (src/gpu_solvers.h:59-64:
+ * tunnel points, WKB tunnel block and its diagonal), preconditioner, rhs = (-loop_G Vd, +loop_G Vd, 0 ...). */
+int kmcb200_assemble_T(kmcb200_ctx *ctx, kmcb200_tmat *tmat, const int *site_element, const int *site_charge,
+                       const double *site_CB_edge, const int *metals_host, int num_metals, double Vd, double high_G,
+                       double low_G, double loop_G, double m_e, double V0);
+/* y = T_neighbor x + scatter(T_tunnel gather(x)): dspmv_split_sparse::spmm_split_sparse1
+ * (dist_iterative/dist_spmv_split_sparse.cpp:5-79).  x, y: N_atom + 1 doubles. */
+int kmcb200_tmat_spmv(kmcb200_ctx *ctx, kmcb200_tmat *tmat, const double *x, double *y);
+/* iterative_solver::conjugate_gradient_jacobi_split_sparse (dist_iterative/dist_conjugate_gradient.h:72-94,
+ * dist_conjugate_gradient_split_sparse.cpp:18-166) on the assembled T with its Jacobi preconditioner.
+ * r: in rhs / out residual; x: warm start in / solution out (N_atom + 1 doubles each). */
+int kmcb200_pcg_jacobi_split_sparse(kmcb200_ctx *ctx, kmcb200_tmat *tmat, double *r, double *x,
+                                    double relative_tolerance, int max_iterations, int *iterations_host);
+/* get_imacro_sparse (src/current_solver_gpu.cu:502-542): sum over the injection row's device columns of
+ * T[1][col] * G0 * (V[col] - V[1]) */
+int kmcb200_imacro(kmcb200_ctx *ctx, kmcb200_tmat *tmat, const double *virtual_potentials, double G0,
+                   double *imacro_host);
+/* assemble + solve (tolerance 1e-30 * N_atom, 100 iterations max, src/current_solver_gpu.cu:1455-1456) + I_macro.
+ * atom_virtual_potentials: N_atom + 1 doubles, warm start in / solution out (gpubuf.atom_virtual_potentials). */
+int kmcb200_update_power_sparse(kmcb200_ctx *ctx, kmcb200_tmat *tmat, const int *site_element, const int *site_charge,
+                                const double *site_CB_edge, const int *metals_host, int num_metals, double Vd,
+                                double high_G, double low_G, double loop_G, double G0, double m_e, double V0,
+                                double *atom_virtual_potentials, double *imacro_host, int *iterations_host);
+
+/* ------------------------------------------------------------------------------------------------
  * Host model (no GPU needed): the pieces of the reference's host side that feed the path and must be
  * read UNCHANGED: parameters.txt grammar (src/input_parser.cpp:3-399), xyz files (src/utils.cpp:72-98),
  * Device::makeSubstoichiometric (src/Device.cpp:180-211), KMCProcess layer assignment

@@ -390,22 +390,22 @@ def tunnel_block(ax, ay, az, a_element, a_cb, metals, nn_dist, num_layers_contac
     return rp, col[:nnz], data[:nnz], diag[:t_count]
 
 
-def split_spmv(row_ptr, col, data, t_row_ptr, t_col, t_data, tunnel_rows, x, lanes=8):
+def split_spmv(row_ptr, col, data, t_row_ptr, t_col, t_data, tunnel_rows, x, lanes=8, t_lanes=32):
     n = len(row_ptr) - 1
     y = np.zeros(n)
     lib().orc_split_spmv(C.c_int(n), _p(_i(row_ptr)), _p(_i(col)), _p(_d(data)), C.c_int(len(tunnel_rows)), _p(_i(t_row_ptr)),
-                         _p(_i(t_col)), _p(_d(t_data)), _p(_i(tunnel_rows)), _p(_d(x)), _p(y), C.c_int(lanes))
+                         _p(_i(t_col)), _p(_d(t_data)), _p(_i(tunnel_rows)), _p(_d(x)), _p(y), C.c_int(lanes), C.c_int(t_lanes))
     return y
 
 
 def pcg_jacobi_split_sparse(row_ptr, col, data, t_row_ptr, t_col, t_data, tunnel_rows, inv_diag, rhs, x0, tol, max_it=100,
-                            lanes=8):
+                            lanes=8, t_lanes=32):
     n = len(row_ptr) - 1
     r = _d(rhs).copy(); x = _d(x0).copy(); stats = np.zeros(2)
     it = lib().orc_pcg_jacobi_split_sparse(C.c_int(n), _p(_i(row_ptr)), _p(_i(col)), _p(_d(data)), C.c_int(len(tunnel_rows)),
                                            _p(_i(t_row_ptr)), _p(_i(t_col)), _p(_d(t_data)), _p(_i(tunnel_rows)),
                                            _p(_d(inv_diag)), _p(r), _p(x), C.c_double(tol), C.c_int(max_it), C.c_int(lanes),
-                                           _p(stats))
+                                           C.c_int(t_lanes), _p(stats))
     return x, r, it, stats
 
 

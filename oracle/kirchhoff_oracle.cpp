@@ -41,6 +41,34 @@ inline double dist_nopbc(double x1, double y1, double z1, double x2, double y2, 
     double dx = x2 - x1, dy = y2 - y1, dz = z2 - z1;
     return std::sqrt(dx * dx + dy * dy + dz * dz);
 }
+// exp / x^1.5 of the WKB coefficients: the summation-spec idea applied to the two transcendental calls of
+// populate_T_tunnel_dist2 (the reference leaves them to the device math library).  Only +, *, fma, sqrt, ldexp: the CUDA
+// kernels evaluate the identical operation sequence (csrc/common.cuh), so the tunnel block is bit-comparable; both agree
+// with libm's exp / pow(x, 1.5) to <= 2 ulp (tests/test_kirchhoff_oracle.py).
+inline double det_exp(double x) {
+    if (!(x > -745.2)) return 0.0;
+    if (x > 709.7) return HUGE_VAL;
+    const double k = std::nearbyint(x * 1.4426950408889634);
+    double r = std::fma(-k, 0.693147180369123816490e+00, x);
+    r = std::fma(-k, 1.90821492927058770002e-10, r);
+    double p = 1.0 / 6227020800.0;
+    p = std::fma(p, r, 1.0 / 479001600.0);
+    p = std::fma(p, r, 1.0 / 39916800.0);
+    p = std::fma(p, r, 1.0 / 3628800.0);
+    p = std::fma(p, r, 1.0 / 362880.0);
+    p = std::fma(p, r, 1.0 / 40320.0);
+    p = std::fma(p, r, 1.0 / 5040.0);
+    p = std::fma(p, r, 1.0 / 720.0);
+    p = std::fma(p, r, 1.0 / 120.0);
+    p = std::fma(p, r, 1.0 / 24.0);
+    p = std::fma(p, r, 1.0 / 6.0);
+    p = std::fma(p, r, 0.5);
+    p = std::fma(p, r, 1.0);
+    p = std::fma(p, r, 1.0);
+    return std::ldexp(p, (int)k);
+}
+inline double det_pow15(double x) { return x * std::sqrt(x); }
+
 inline bool is_metal(int el, const int *metals, int num_metals) {
     for (int m = 0; m < num_metals; ++m)
         if (metals[m] == el) return true;
@@ -49,6 +77,10 @@ inline bool is_metal(int el, const int *metals, int num_metals) {
 }  // namespace
 
 extern "C" {
+
+// test hooks for the deterministic math routines
+double orc_det_exp(double x) { return det_exp(x); }
+double orc_det_pow15(double x) { return det_pow15(x); }
 
 // update_atom_arrays: the sites that are neither DEFECT nor OXYGEN_DEFECT, in site order.  atom_ind_out may be NULL.
 int orc_atoms_compact(int N, const int *element, int *atom_ind_out) {
@@ -247,8 +279,8 @@ inline double tunnel_value(double dist_angstrom, double local_E_drop, bool conta
             double E1 = eV_to_J * V0 + iv;
             double E2 = E1 - std::fabs(local_E_drop);
             double term = -1.0;
-            if (E2 > 0) term = std::exp(prefac * (dist / std::fabs(local_E_drop)) * (std::pow(E1, 1.5) - std::pow(E2, 1.5)));
-            if (E2 < 0) term = std::exp(prefac * (dist / std::fabs(local_E_drop)) * (std::pow(E1, 1.5)));
+            if (E2 > 0) term = det_exp(prefac * (dist / std::fabs(local_E_drop)) * (det_pow15(E1) - det_pow15(E2)));
+            if (E2 < 0) term = det_exp(prefac * (dist / std::fabs(local_E_drop)) * (det_pow15(E1)));
             if (term >= 0.0) {
                 T += term;
                 if (term == 0.0) break;
@@ -258,8 +290,8 @@ inline double tunnel_value(double dist_angstrom, double local_E_drop, bool conta
     }
     double E1 = eV_to_J * V0;
     double E2 = E1 - std::fabs(local_E_drop);
-    if (E2 > 0) return -std::exp(prefac * (dist / std::fabs(E1 - E2)) * (std::pow(E1, 1.5) - std::pow(E2, 1.5)));
-    if (E2 < 0) return -std::exp(prefac * (dist / std::fabs(E1 - E2)) * (std::pow(E1, 1.5)));
+    if (E2 > 0) return -det_exp(prefac * (dist / std::fabs(E1 - E2)) * (det_pow15(E1) - det_pow15(E2)));
+    if (E2 < 0) return -det_exp(prefac * (dist / std::fabs(E1 - E2)) * (det_pow15(E1)));
     *written = false;  // E2 == 0: the reference leaves the (uninitialised) entry untouched; defined as 0 here
     return 0.0;
 }
@@ -322,11 +354,11 @@ long orc_tunnel_block(int N_atom, const double *ax, const double *ay, const doub
 // tunnel_rows[t] = matrix row of tunnel point t (= tunnel_atoms[t] + 2).
 void orc_split_spmv(int n, const int *row_ptr, const int *col, const double *data, int n_tunnel, const int *t_row_ptr,
                     const int *t_col, const double *t_data, const int *tunnel_rows, const double *x, double *y,
-                    int lanes) {
+                    int lanes, int t_lanes) {
     orc_spmv(n, row_ptr, col, data, x, y, lanes);
     std::vector<double> xs((size_t)std::max(n_tunnel, 1)), ys((size_t)std::max(n_tunnel, 1));
     for (int t = 0; t < n_tunnel; ++t) xs[t] = x[tunnel_rows[t]];  // pack_gpu
-    orc_spmv(n_tunnel, t_row_ptr, t_col, t_data, xs.data(), ys.data(), lanes);
+    orc_spmv(n_tunnel, t_row_ptr, t_col, t_data, xs.data(), ys.data(), t_lanes);  // tunnel rows are long: 32 lanes per row
     for (int t = 0; t < n_tunnel; ++t) y[tunnel_rows[t]] = y[tunnel_rows[t]] + ys[t];  // unpack_add
 }
 
@@ -334,10 +366,10 @@ void orc_split_spmv(int n, const int *row_ptr, const int *col, const double *dat
 int orc_pcg_jacobi_split_sparse(int n, const int *row_ptr, const int *col, const double *data, int n_tunnel,
                                 const int *t_row_ptr, const int *t_col, const double *t_data, const int *tunnel_rows,
                                 const double *inv_diag, double *r, double *x, double tol, int max_it, int lanes,
-                                double *stats) {
+                                int t_lanes, double *stats) {
     std::vector<double> p((size_t)n), Ap((size_t)n), z((size_t)n);
     double bb = orc_dot(r, r, n);
-    orc_split_spmv(n, row_ptr, col, data, n_tunnel, t_row_ptr, t_col, t_data, tunnel_rows, x, Ap.data(), lanes);
+    orc_split_spmv(n, row_ptr, col, data, n_tunnel, t_row_ptr, t_col, t_data, tunnel_rows, x, Ap.data(), lanes, t_lanes);
     for (int i = 0; i < n; ++i) { r[i] = r[i] - Ap[i]; z[i] = r[i] * inv_diag[i]; }
     double rz = orc_dot(r, z.data(), n), r0 = 0.0;
     int k = 1;
@@ -348,7 +380,7 @@ int orc_pcg_jacobi_split_sparse(int n, const int *row_ptr, const int *col, const
         } else {
             for (int i = 0; i < n; ++i) p[i] = z[i];
         }
-        orc_split_spmv(n, row_ptr, col, data, n_tunnel, t_row_ptr, t_col, t_data, tunnel_rows, p.data(), Ap.data(), lanes);
+        orc_split_spmv(n, row_ptr, col, data, n_tunnel, t_row_ptr, t_col, t_data, tunnel_rows, p.data(), Ap.data(), lanes, t_lanes);
         double pAp = orc_dot(p.data(), Ap.data(), n);
         double a = rz / pAp, na = -a;
         for (int i = 0; i < n; ++i) {

@@ -116,3 +116,24 @@ def test_current_solution(orc, s5, ko5):
     it2 = ko.solve()                                   # warm start from the previous solution (gpubuf.atom_virtual_potentials)
     # (conductance contrast 1e13 and 100 iterations: the oxide potentials are still moving; the driven nodes are not)
     assert it2 <= 100 and np.isfinite(ko.x).all() and np.abs(ko.x[:2] - x_first[:2]).max() < 1e-3 * s5.Vd
+
+
+def test_deterministic_exp_and_pow15_track_libm(orc):
+    """the shared exp / x^1.5 of the WKB coefficients agree with libm to <= 2 ulp over the range the tunnel block uses"""
+    import ctypes as C
+    import math
+    L = orc.lib()
+    L.orc_det_exp.restype = C.c_double; L.orc_det_pow15.restype = C.c_double
+    rng = np.random.default_rng(7)
+    xs = np.concatenate([rng.uniform(-740, 5, 20000), rng.uniform(-1e-3, 1e-3, 2000), [0.0, -0.0, -745.0, -745.3, -1e4]])
+    worst = 0.0
+    for x in xs:
+        got, want = L.orc_det_exp(C.c_double(x)), math.exp(x) if x > -745.2 else 0.0
+        if want > 1e-300:
+            worst = max(worst, abs(got - want) / (np.spacing(want)))
+        else:
+            assert abs(got - want) <= 1e-300
+    assert worst <= 2.0, worst
+    es = 10.0 ** rng.uniform(-22, -17, 5000)
+    w2 = max(abs(L.orc_det_pow15(C.c_double(e)) - e ** 1.5) / np.spacing(e ** 1.5) for e in es)
+    assert w2 <= 2.0, w2
