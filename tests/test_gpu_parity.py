@@ -361,6 +361,32 @@ def test_cpp_host_driver_reproduces_golden_output(kmc, tmp_path):
     assert init[:37652] == ginit[:37652]   # byte-identical initial snapshot (same ostream formatting)
 
 
+def test_cpp_host_driver_runs_the_current_solver(kmc, orc, s5, tmp_path):
+    """With comm_T kept alive (KMCB200_ENABLE_CURRENT=1; the reference forces it to MPI_COMM_NULL, src/KMC_comm.h:243) the C++
+    host runs setLaplacePotential -> initialize_sparsity_T -> update_power_gpu_sparse_dist through the reference-named
+    entry points and logs the macroscopic current: the first superstep's value against the oracle chain."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(kmc.LIB_PATH), "kmc_b200_run")
+    if not os.path.exists(exe):
+        pytest.skip("kmc_b200_run not built")
+    env = dict(os.environ, KMCB200_ENABLE_CURRENT="1")
+    r = subprocess.run([exe, os.path.join(GOLD, "5nm_device", "parameters.txt"), "2"], cwd=tmp_path, capture_output=True,
+                       text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = open(tmp_path / "output1_0.txt").read()
+    im = [float(l.split(":")[1]) for l in out.split("\n") if l.startswith("I_macro")]
+    assert len(im) == 2
+    sim = orc.OracleSim(s5, use_cells=True)
+    ch = orc.update_charge(s5.element, np.zeros(s5.N, np.int32), sim.neigh, s5.metals)
+    ko = orc.KirchhoffOracle(s5, sim.sp, 10, site_charge=ch)
+    ko.solve()
+    assert abs(im[0] - ko.imacro * 1e6) <= 2e-5 * abs(ko.imacro * 1e6)    # printed with 6 significant digits
+    # the KMC trajectory is unchanged by the current solver
+    mine = [float(l.split(":")[1]) for l in out.split("\n") if l.startswith("KMC time is")]
+    gold = [float(l.split(":")[1]) for l in open(os.path.join(GOLD, "5nm_device", "output1_0.txt")) if l.startswith("KMC time is")]
+    assert np.allclose(mine, gold[:2], rtol=1e-3)
+
+
 # ---------------------------------------------------------------- edge cases
 def test_edge_empty_ranges_and_bad_arguments(kmc, ctx, s_small):
     s = s_small
