@@ -44,6 +44,7 @@ int comm_alloc(kmcb200_comm *c) {
     c->off_p[0] = off; off = align_up(off + n * sizeof(double), 256);
     c->off_p[1] = off; off = align_up(off + n * sizeof(double), 256);
     c->off_partials = off; off = align_up(off + (size_t)KMC_DOT_SLOTS * c->nchunks_global * sizeof(double), 256);
+    c->off_gtotals = off; off = align_up(off + (size_t)KMC_DOT_SLOTS * (c->ngroups_global + 1) * sizeof(double), 256);
     c->off_flag_dot = off; off += 256;
     c->off_flag_halo = off; off += 256;
     c->arena_bytes = align_up(off, 2 << 20);
@@ -70,6 +71,10 @@ void kmc_comm_fill_dev(kmcb200_comm *c) {
     d.p_full[0] = (double *)(c->arena + c->off_p[0]);
     d.p_full[1] = (double *)(c->arena + c->off_p[1]);
     d.partials = (double *)(c->arena + c->off_partials);
+    d.group_chunks = c->group_chunks;
+    d.ngroups_global = c->ngroups_global;
+    d.group_start = c->group_chunks ? d.chunk_start / c->group_chunks : 0;
+    d.gtotals = (double *)(c->arena + c->off_gtotals);
     d.flag_dot = (unsigned long long *)(c->arena + c->off_flag_dot);
     d.flag_halo = (unsigned long long *)(c->arena + c->off_flag_halo);
     for (int q = 0; q < KMC_MAX_RANKS; ++q) {
@@ -77,10 +82,12 @@ void kmc_comm_fill_dev(kmcb200_comm *c) {
         d.peer_p_full[q][0] = base ? (double *)(base + c->off_p[0]) : nullptr;
         d.peer_p_full[q][1] = base ? (double *)(base + c->off_p[1]) : nullptr;
         d.peer_partials[q] = base ? (double *)(base + c->off_partials) : nullptr;
+        d.peer_gtotals[q] = base ? (double *)(base + c->off_gtotals) : nullptr;
         d.peer_flag_dot[q] = base ? (unsigned long long *)(base + c->off_flag_dot) : nullptr;
         d.peer_flag_halo[q] = base ? (unsigned long long *)(base + c->off_flag_halo) : nullptr;
     }
     d.send_mask = c->send_mask;
+    if (d.timeout_ns == 0) d.timeout_ns = 20000000000ull;  // 20 s until kmcb200_pcg_jacobi sets the configured bound
 }
 
 int kmc_comm_create_local(kmcb200_ctx *ctx, int n_rows, kmcb200_comm **out) {
@@ -93,10 +100,13 @@ extern "C" int kmcb200_comm_create(kmcb200_ctx *ctx, int rank, int size, int n_g
     KMC_CHECK_ARG(ctx && counts && displs && comm_out, "null pointer");
     KMC_CHECK_ARG(size >= 1 && size <= KMC_MAX_RANKS && rank >= 0 && rank < size, "rank/size (<= 8 ranks)");
     long long sum = 0;
+    const int nchunks_g = (n_global_rows + KMCB200_CHUNK - 1) / KMCB200_CHUNK;
+    const int gran = (nchunks_g > 256 ? KMCB200_DOT_GROUP : 1) * KMCB200_CHUNK;
     for (int q = 0; q < size; ++q) {
         KMC_CHECK_ARG(displs[q] == sum, "displs must be the prefix sums of counts");
-        KMC_CHECK_ARG(size == 1 || displs[q] % KMCB200_CHUNK == 0 || counts[q] == 0,
-                      "rank boundaries must be multiples of 256 rows (kmcb200_partition_aligned)");
+        KMC_CHECK_ARG(size == 1 || displs[q] % gran == 0 || counts[q] == 0,
+                      "rank boundaries must be multiples of 256 rows (16384 rows for systems of more than 65536 rows): "
+                      "kmcb200_partition_aligned");
         sum += counts[q];
     }
     KMC_CHECK_ARG(sum == n_global_rows, "counts do not add up to n_global_rows");
@@ -106,6 +116,8 @@ extern "C" int kmcb200_comm_create(kmcb200_ctx *ctx, int rank, int size, int n_g
     c->size = size;
     c->n_global = n_global_rows;
     c->nchunks_global = (n_global_rows + KMCB200_CHUNK - 1) / KMCB200_CHUNK;
+    c->group_chunks = c->nchunks_global > 256 ? KMCB200_DOT_GROUP : 0;
+    c->ngroups_global = c->group_chunks ? (c->nchunks_global + c->group_chunks - 1) / c->group_chunks : 0;
     c->counts.assign(counts, counts + size);
     c->displs.assign(displs, displs + size);
     int rc = comm_alloc(c);
@@ -195,6 +207,7 @@ extern "C" int kmcb200_comm_set_send_masks(kmcb200_comm *c, const unsigned char 
     KMC_CUDA(cudaMemcpyAsync(&m, d_mask, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
     KMC_CUDA(cudaStreamSynchronize(ctx->stream));
     c->recv_mask = m & ~(1u << c->rank);
+    c->masks_set = true;
     kmc_comm_fill_dev(c);
     return 0;
 }

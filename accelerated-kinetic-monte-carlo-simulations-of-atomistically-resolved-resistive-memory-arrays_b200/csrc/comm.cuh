@@ -24,7 +24,12 @@ struct CommDev {
     int chunk_start;          // row_start / 256
     unsigned recv_mask;       // peers this rank's matrix rows read p entries from
     double *p_full[2];        // local, double buffered, indexed by global row
-    double *partials;         // local, KMC_DOT_SLOTS * nchunks_global
+    double *partials;         // local, KMC_DOT_SLOTS * nchunks_global (chunk partials; exchanged only when group_chunks == 0)
+    int group_chunks;         // 0: single-level dot combine (<= 256 chunks); else KMCB200_DOT_GROUP
+    int ngroups_global;       // ceil(nchunks_global / group_chunks) (0 when single-level)
+    int group_start;          // chunk_start / group_chunks
+    double *gtotals;          // local, KMC_DOT_SLOTS * ngroups_global: the group totals of ALL ranks
+    double *peer_gtotals[KMC_MAX_RANKS];
     unsigned long long *flag_dot;   // local, [KMC_MAX_RANKS] written by peers
     unsigned long long *flag_halo;  // local, [KMC_MAX_RANKS] written by peers
     double *peer_p_full[KMC_MAX_RANKS][2];
@@ -32,6 +37,8 @@ struct CommDev {
     unsigned long long *peer_flag_dot[KMC_MAX_RANKS];   // peer's flag_dot array (we write entry [rank])
     unsigned long long *peer_flag_halo[KMC_MAX_RANKS];
     const unsigned char *send_mask;  // local rows: bit q set -> peer q needs this row's p entry
+    unsigned long long timeout_ns;   // bound of every peer-flag wait
+    int *err;                        // device word raised when a wait timed out (CgState::comm_error of the context)
 };
 
 struct kmcb200_comm {
@@ -41,7 +48,9 @@ struct kmcb200_comm {
     std::vector<int> counts, displs;
     char *arena = nullptr;  // local allocation shared with the peers through CUDA IPC
     size_t arena_bytes = 0;
-    size_t off_p[2] = {0, 0}, off_partials = 0, off_flag_dot = 0, off_flag_halo = 0;
+    size_t off_p[2] = {0, 0}, off_partials = 0, off_gtotals = 0, off_flag_dot = 0, off_flag_halo = 0;
+    int group_chunks = 0, ngroups_global = 0;
+    bool masks_set = false;  // kmcb200_comm_set_send_masks was called (required before any sharded SpMV / PCG)
     char *peer_arena[KMC_MAX_RANKS] = {nullptr};
     bool peers_open = false;
     unsigned char *send_mask = nullptr;  // counts[rank] bytes
@@ -65,11 +74,32 @@ __device__ __forceinline__ unsigned long long kmc_load_relaxed_sys(const unsigne
     asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-// one thread waits until every peer in `mask` has published sequence number >= seq (caller fences afterwards)
-__device__ __forceinline__ void kmc_wait_flags(const unsigned long long *flags, unsigned mask, int self,
-                                               unsigned long long seq) {
+__device__ __forceinline__ unsigned long long kmc_globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// One thread waits until every peer in `mask` has published sequence number >= seq (caller fences afterwards).
+// The wait is BOUNDED: if a peer never arrives (it left the solve early, its process died) the waiter gives up after
+// timeout_ns, raises *err and returns false; the kernels of the solve then wind down (CgState::done) and the host call
+// returns KMCB200_E_COMM instead of leaving every GPU of the job spinning.
+__device__ __forceinline__ bool kmc_wait_flags(const unsigned long long *flags, unsigned mask, int self,
+                                               unsigned long long seq, unsigned long long timeout_ns, int *err) {
+    unsigned long long deadline = 0;
     for (int q = 0; q < KMC_MAX_RANKS; ++q) {
         if (q == self || !((mask >> q) & 1u)) continue;
-        while (kmc_load_relaxed_sys(flags + q) < seq) { __nanosleep(20); }
+        unsigned spins = 0;
+        while (kmc_load_relaxed_sys(flags + q) < seq) {
+            __nanosleep(20);
+            if ((++spins & 1023u) == 0) {
+                const unsigned long long now = kmc_globaltimer_ns();
+                if (deadline == 0) deadline = now + timeout_ns;
+                else if (now > deadline || (err && *(volatile int *)err)) {
+                    if (err) *(volatile int *)err = 1;
+                    return false;
+                }
+            }
+        }
     }
+    return true;
 }

@@ -14,7 +14,7 @@
 
 struct CgState {
     double bb, rz, rz_old, pAp, tol2, scalar_out;
-    int k, max_it, done, iters;
+    int k, max_it, done, iters, comm_error;  // comm_error: a peer-flag wait timed out (the solve is abandoned)
     unsigned cnt[8];
 };
 
@@ -69,46 +69,101 @@ __device__ __forceinline__ void exchange_partials(const CommDev &cm, int slot0, 
         if (threadIdx.x == 0) {
             for (int q = 0; q < cm.size; ++q)
                 if (q != cm.rank) kmc_store_relaxed_sys(cm.peer_flag_dot[q] + cm.rank, seq);
-            kmc_wait_flags(cm.flag_dot, (1u << cm.size) - 1u, cm.rank, seq);
+            kmc_wait_flags(cm.flag_dot, (1u << cm.size) - 1u, cm.rank, seq, cm.timeout_ns, cm.err);
             __threadfence_system();
         }
         __syncthreads();
     }
 }
-// ---- completion of a dot product: exchange the partials with the peers, reduce ALL partials in the fixed order, update
-// the PCG state.  Runs either in the last CTA of the producing kernel (small problems: saves a launch) or in the 1-CTA
-// dot_finalize_kernel (large problems: the producing kernel's CTAs then need no fence / atomic at all).
+// Level 1 of the two-level dot combine (systems with more than 256 chunks): each warp reduces whole groups of 64 local
+// chunk partials (group = chunk_reduce_256 of the 64 values padded with zeros = the two warp butterflies added, then six
+// exact "+ 0.0"), stores the total in this rank's table of ALL group totals and in every peer's table.
+__device__ __forceinline__ void reduce_and_push_groups(const CommDev &cm, int slot0, int nslots, int local_chunks) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int local_groups = (local_chunks + KMCB200_DOT_GROUP - 1) / KMCB200_DOT_GROUP;
+    for (int sidx = 0; sidx < nslots; ++sidx) {
+        const double *part = cm.partials + (size_t)(slot0 + sidx) * cm.nchunks_global + cm.chunk_start;
+        const size_t gbase = (size_t)(slot0 + sidx) * cm.ngroups_global + cm.group_start;
+        for (int g = w; g < local_groups; g += nw) {
+            const int c0 = g * KMCB200_DOT_GROUP + lane;
+            const double v0 = (c0 < local_chunks) ? __ldcg(part + c0) : 0.0;
+            const double v1 = (c0 + 32 < local_chunks) ? __ldcg(part + c0 + 32) : 0.0;
+            double tot = kmc_warp_xor_sum(v0);
+            tot = tot + kmc_warp_xor_sum(v1);
+#pragma unroll
+            for (int q = 0; q < 6; ++q) tot = tot + 0.0;  // the six empty warps of chunk_reduce_256
+            if (lane == 0) {
+                cm.gtotals[gbase + g] = tot;
+                for (int q = 0; q < cm.size; ++q)
+                    if (q != cm.rank) cm.peer_gtotals[q][gbase + g] = tot;
+            }
+        }
+    }
+}
+// completes `nslots` dot products at once: exchange (chunk partials for small systems, group totals for large ones), one
+// flag round trip, then the fixed-order reduction.  All threads of a 256-thread CTA; out[] valid in thread 0.
+__device__ __forceinline__ void finish_dots(const CommDev &cm, int slot0, int nslots, int local_chunks,
+                                            unsigned long long seq, double *red, double *out) {
+    if (cm.group_chunks == 0) {
+        exchange_partials(cm, slot0, nslots, local_chunks, seq);
+        for (int sidx = 0; sidx < nslots; ++sidx)
+            out[sidx] = kmc_final_reduce(cm.partials + (size_t)(slot0 + sidx) * cm.nchunks_global, cm.nchunks_global, red);
+        return;
+    }
+    reduce_and_push_groups(cm, slot0, nslots, local_chunks);
+    if (cm.size > 1) {
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int q = 0; q < cm.size; ++q)
+                if (q != cm.rank) kmc_store_relaxed_sys(cm.peer_flag_dot[q] + cm.rank, seq);
+            kmc_wait_flags(cm.flag_dot, (1u << cm.size) - 1u, cm.rank, seq, cm.timeout_ns, cm.err);
+            __threadfence_system();
+        }
+    } else {
+        __threadfence();
+    }
+    __syncthreads();
+    for (int sidx = 0; sidx < nslots; ++sidx)
+        out[sidx] = kmc_final_reduce(cm.gtotals + (size_t)(slot0 + sidx) * cm.ngroups_global, cm.ngroups_global, red);
+}
+// ---- completion of a dot product: exchange with the peers, reduce in the fixed order, update the PCG state.  Runs either
+// in the last CTA of the producing kernel (small problems: saves a launch) or in the 1-CTA dot_finalize_kernel (large
+// problems: the producing kernel's CTAs then need no fence / atomic at all).
 __device__ __forceinline__ void finish_pap(const CommDev &cm, int local_chunks, unsigned long long seq, CgState *st,
                                            double *red) {
-    exchange_partials(cm, 0, 1, local_chunks, seq);
-    double tot = kmc_final_reduce(cm.partials, cm.nchunks_global, red);
-    if (threadIdx.x == 0) st->pAp = tot;
+    double tot;
+    finish_dots(cm, 0, 1, local_chunks, seq, red, &tot);
+    if (threadIdx.x == 0) {
+        st->pAp = tot;
+        if (cm.err && *(volatile int *)cm.err) st->done = 1;
+    }
 }
 __device__ __forceinline__ void finish_rz(const CommDev &cm, int local_chunks, unsigned long long seq, CgState *st,
                                           double *red) {
-    exchange_partials(cm, 1, 1, local_chunks, seq);
-    double rz = kmc_final_reduce(cm.partials + (size_t)cm.nchunks_global, cm.nchunks_global, red);
+    double rz;
+    finish_dots(cm, 1, 1, local_chunks, seq, red, &rz);
     if (threadIdx.x == 0) {
         st->rz_old = st->rz;
         st->rz = rz;
         int k = st->k + 1;
         st->k = k;
         st->iters = k - 1;
-        st->done = !(rz / st->bb > st->tol2 && k <= st->max_it);
+        st->done = !(rz / st->bb > st->tol2 && k <= st->max_it) || (cm.err && *(volatile int *)cm.err);
     }
 }
 __device__ __forceinline__ void finish_init(const CommDev &cm, int local_chunks, unsigned long long seq, CgState *st,
                                             double *red) {
-    exchange_partials(cm, 2, 2, local_chunks, seq);
-    double bb = kmc_final_reduce(cm.partials + (size_t)2 * cm.nchunks_global, cm.nchunks_global, red);
-    double rz = kmc_final_reduce(cm.partials + (size_t)3 * cm.nchunks_global, cm.nchunks_global, red);
+    double o[2];
+    finish_dots(cm, 2, 2, local_chunks, seq, red, o);
     if (threadIdx.x == 0) {
+        const double bb = o[0], rz = o[1];
         st->bb = bb;
         st->rz = rz;
         st->rz_old = 0.0;
         st->k = 1;
         st->iters = 0;
-        st->done = !(rz / bb > st->tol2 && 1 <= st->max_it);
+        st->done = !(rz / bb > st->tol2 && 1 <= st->max_it) || (cm.err && *(volatile int *)cm.err);
     }
 }
 // kind: 0 = p.Ap, 1 = r.z (+ iteration bookkeeping), 2 = setup (b.b and r.z)
@@ -345,7 +400,7 @@ __global__ void __launch_bounds__(CH) cg_pupdate_kernel(int rows, int nchunks, c
                 __threadfence_system();
                 for (int q = 0; q < cm.size; ++q)
                     if (q != cm.rank) kmc_store_relaxed_sys(cm.peer_flag_halo[q] + cm.rank, halo_seq);
-                kmc_wait_flags(cm.flag_halo, cm.recv_mask, cm.rank, halo_seq);
+                if (!kmc_wait_flags(cm.flag_halo, cm.recv_mask, cm.rank, halo_seq, cm.timeout_ns, cm.err)) st->done = 1;
                 __threadfence_system();
                 st->cnt[4] = 0;
             }
@@ -457,7 +512,28 @@ __global__ void __launch_bounds__(CH) dot_kernel(long long n, const double *__re
     double c = kmc_chunk_reduce_256(p, red);
     if (threadIdx.x == 0) partials[blockIdx.x] = c;
     if (last_cta(&st->cnt[3], &flag, false)) {
-        double tot = kmc_final_reduce(partials, gridDim.x, red);
+        const int nchunks = (int)gridDim.x;
+        double tot;
+        if (nchunks <= 256) {
+            tot = kmc_final_reduce(partials, nchunks, red);
+        } else {  // two-level combine of the summation spec: group totals behind the partials
+            double *gt = partials + nchunks;
+            const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+            const int ngroups = (nchunks + KMCB200_DOT_GROUP - 1) / KMCB200_DOT_GROUP;
+            for (int g = w; g < ngroups; g += CH / 32) {
+                const int c0 = g * KMCB200_DOT_GROUP + lane;
+                const double v0 = (c0 < nchunks) ? __ldcg(partials + c0) : 0.0;
+                const double v1 = (c0 + 32 < nchunks) ? __ldcg(partials + c0 + 32) : 0.0;
+                double t = kmc_warp_xor_sum(v0);
+                t = t + kmc_warp_xor_sum(v1);
+#pragma unroll
+                for (int q = 0; q < 6; ++q) t = t + 0.0;
+                if (lane == 0) gt[g] = t;
+            }
+            __threadfence();
+            __syncthreads();
+            tot = kmc_final_reduce(gt, ngroups, red);
+        }
         if (threadIdx.x == 0) {
             st->scalar_out = tot;
             st->cnt[3] = 0;
@@ -550,6 +626,10 @@ extern "C" int kmcb200_spmv(kmcb200_ctx *ctx, kmcb200_kmat *K, const double *x_l
     KMC_TRY(ensure_cg_workspace(ctx, 1));
     static const bool force_dot = getenv("KMCB200_SPMV_FORCE_DOT") != nullptr;  // diagnostics: time the dot variant
     if (K->comm->size == 1) return spmv_launch(ctx, K, x_local, y_local, force_dot, 0, 0);
+    if (!(K->comm->peers_open && K->comm->masks_set)) {
+        kmc_set_error("row-sharded SpMV: kmcb200_comm_open_peers and kmcb200_comm_set_send_masks must be called first");
+        return KMCB200_E_COMM;
+    }
     int buf;
     unsigned long long hs;
     KMC_TRY(push_vector(ctx, K, x_local, &buf, &hs));
@@ -632,14 +712,19 @@ int kmc_pcg_run(kmcb200_ctx *ctx, kmcb200_kmat *K, const TunnelDev *tun, double 
     KMC_CHECK_ARG(K->comm != nullptr, "kmat has no exchange plan");
     kmcb200_comm *C = K->comm;
     KMC_CHECK_ARG(tun == nullptr || C->size == 1, "split-sparse PCG with a tunnel block: single-rank call");
-    if (C->size > 1 && !C->peers_open) {
-        kmc_set_error("row-sharded PCG: kmcb200_comm_open_peers / kmcb200_comm_set_send_masks were not called");
+    if (C->size > 1 && !(C->peers_open && C->masks_set)) {
+        kmc_set_error("row-sharded PCG: kmcb200_comm_open_peers and kmcb200_comm_set_send_masks must be called first");
         return KMCB200_E_COMM;
     }
     const int rows = K->rows;
     const unsigned nchunks = (unsigned)((rows + CH - 1) / CH);
     KMC_TRY(ensure_cg_workspace(ctx, nchunks));
     CgState *st = ctx->cg_state;
+    {   // bounded peer waits (comm.cuh): error word in the solver state, timeout from the environment (default 20 s)
+        static const double tmo_ms = getenv("KMCB200_COMM_TIMEOUT_MS") ? atof(getenv("KMCB200_COMM_TIMEOUT_MS")) : 20000.0;
+        C->dev.err = &st->comm_error;
+        C->dev.timeout_ns = (unsigned long long)(tmo_ms * 1e6);
+    }
     // host-initialised part of the state (counters stay 0 between launches)
     CgState *h = (CgState *)ctx->h_mail;
     memset(h, 0, sizeof(CgState));
@@ -675,8 +760,13 @@ int kmc_pcg_run(kmcb200_ctx *ctx, kmcb200_kmat *K, const TunnelDev *tun, double 
     KMC_CUDA(cudaGetLastError());
     int *h_flags = (int *)((char *)ctx->h_mail + 512);
     auto read_flags = [&]() -> int {
-        KMC_CUDA(cudaMemcpyAsync(h_flags, &st->k, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        KMC_CUDA(cudaMemcpyAsync(h_flags, &st->k, 5 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         KMC_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (h_flags[4]) {  // CgState::comm_error
+            kmc_set_error("row-sharded PCG: rank %d waited more than %.0f ms for a peer's flag (a peer left the solve or died)",
+                          C->rank, (double)C->dev.timeout_ns * 1e-6);
+            return KMCB200_E_COMM;
+        }
         return 0;
     };
     KMC_TRY(read_flags());

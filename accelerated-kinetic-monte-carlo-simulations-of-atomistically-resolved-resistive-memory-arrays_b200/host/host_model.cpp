@@ -322,12 +322,15 @@ extern "C" void kmcb200_partition(int nrows, int nranks, int *counts, int *displ
 }
 
 extern "C" void kmcb200_partition_aligned(int nrows, int nranks, int *counts, int *displs) {
-    int nchunks = (nrows + KMCB200_CHUNK - 1) / KMCB200_CHUNK;
-    int per = nchunks / nranks;
+    const int nchunks = (nrows + KMCB200_CHUNK - 1) / KMCB200_CHUNK;
+    // granule: one dot chunk, or one dot GROUP of chunks for systems whose dots are combined in two levels
+    const int gran = (nchunks > 256 ? KMCB200_DOT_GROUP : 1) * KMCB200_CHUNK;
+    const int ngran = (nrows + gran - 1) / gran;
+    int per = ngran / nranks;
     int acc = 0;
     for (int i = 0; i < nranks; ++i) {
-        int c = per + (i < nchunks % nranks ? 1 : 0);
-        int rows = c * KMCB200_CHUNK;
+        int c = per + (i < ngran % nranks ? 1 : 0);
+        int rows = c * gran;
         if (acc + rows > nrows) rows = nrows - acc;
         if (rows < 0) rows = 0;
         displs[i] = acc;

@@ -45,10 +45,17 @@ def recv_mask_numpy(my_need: np.ndarray, rank: int, counts, displs) -> int:
     return mask
 
 
-def balanced_partition(row_weight: np.ndarray, nranks: int, chunk: int = 256):
-    """Contiguous row blocks with boundaries on multiples of `chunk` rows and (nearly) equal total weight (non-zeros).
-    Any chunk-aligned partition gives bit-identical results; this one also balances the SpMV."""
+def dot_granule(n_rows: int) -> int:
+    """rows between allowed rank boundaries: one 256-row dot chunk, or one 64-chunk dot group (16 384 rows) for systems
+    whose dot products are combined in two levels (more than 256 chunks), kmc_b200.h KMCB200_DOT_GROUP"""
+    return 256 if (n_rows + 255) // 256 <= 256 else 64 * 256
+
+
+def balanced_partition(row_weight: np.ndarray, nranks: int, chunk: int = 0):
+    """Contiguous row blocks with boundaries on multiples of the dot granule and (nearly) equal total weight (non-zeros).
+    Any granule-aligned partition gives bit-identical results; this one also balances the SpMV."""
     n = len(row_weight)
+    chunk = chunk or dot_granule(n)
     nch = (n + chunk - 1) // chunk
     pad = np.zeros(nch * chunk, dtype=np.int64)
     pad[:n] = row_weight

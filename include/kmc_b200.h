@@ -47,6 +47,7 @@ enum { KMCB200_VACANCY_GENERATION = 0, KMCB200_VACANCY_RECOMBINATION = 1, KMCB20
 #define KMCB200_MAX_METALS 4
 #define KMCB200_CHUNK 256      /* rows per deterministic dot-product chunk  */
 #define KMCB200_SPMV_LANES 8   /* lanes per CSR row in the SpMV row reduction */
+#define KMCB200_DOT_GROUP 64   /* chunks per group of the two-level dot combine (systems with more than 256 chunks) */
 
 typedef struct kmcb200_ctx kmcb200_ctx;        /* device + stream + scratch                         */
 typedef struct kmcb200_kmat kmcb200_kmat;      /* K matrix: reference Distributed_matrix + contact CSR */
@@ -322,8 +323,8 @@ int kmcb200_layer_table(double *E_gen, double *E_rec, double *E_Vdiff, double *E
                         double *end_x);
 int kmcb200_assign_layers(int N, const double *x, int *site_layer);
 void kmcb200_partition(int nrows, int nranks, int *counts, int *displs);
-/* partition with chunk-aligned boundaries (multiples of KMCB200_CHUNK): makes multi-GPU dot products
- * bit-identical to 1 GPU */
+/* partition whose boundaries keep multi-GPU dot products bit-identical to 1 GPU: multiples of
+ * KMCB200_CHUNK rows for systems of up to 256 chunks, multiples of KMCB200_DOT_GROUP chunks (16 384 rows) above */
 void kmcb200_partition_aligned(int nrows, int nranks, int *counts, int *displs);
 
 #ifdef __cplusplus

@@ -173,6 +173,26 @@ inline double final_reduce(const double *partials, long n) {
     return chunk_reduce_256(s);
 }
 
+// Cross-chunk combine of the dot products (summation spec).  Up to 256 chunks (65 536 rows): the
+// single-level final_reduce.  Above: two levels -- groups of ORC_DOT_GROUP = 64 consecutive chunks are reduced first (a
+// group = chunk_reduce_256 of its 64 partials padded with zeros), then final_reduce runs over the group totals.  On
+// several GPUs only the group totals cross NVLink (64x fewer values than the chunk partials); the result is independent
+// of the GPU count when rank boundaries are multiples of 64 chunks.
+double combine_partials(const double *partials, long nchunks) {
+    if (nchunks <= 256) return final_reduce(partials, nchunks);
+    long ngroups = (nchunks + ORC_DOT_GROUP - 1) / ORC_DOT_GROUP;
+    std::vector<double> gt((size_t)ngroups);
+    for (long g = 0; g < ngroups; ++g) {
+        double v[256];
+        for (int t = 0; t < 256; ++t) {
+            long c = g * ORC_DOT_GROUP + t;
+            v[t] = (t < ORC_DOT_GROUP && c < nchunks) ? partials[c] : 0.0;
+        }
+        gt[g] = chunk_reduce_256(v);
+    }
+    return final_reduce(gt.data(), ngroups);
+}
+
 double dot_spec(const double *u, const double *v, long n) {
     long nchunks = (n + ORC_CHUNK - 1) / ORC_CHUNK;
     std::vector<double> partials((size_t)std::max<long>(nchunks, 1), 0.0);
@@ -185,7 +205,7 @@ double dot_spec(const double *u, const double *v, long n) {
         }
         partials[c] = chunk_reduce_256(vals);
     }
-    return final_reduce(partials.data(), nchunks);
+    return combine_partials(partials.data(), nchunks);
 }
 
 void spmv_spec(long n, const int *row_ptr, const int *col, const double *data, const double *x, double *y,

@@ -36,6 +36,7 @@ enum { ORC_VACANCY_GENERATION = 0, ORC_VACANCY_RECOMBINATION = 1, ORC_VACANCY_DI
 #define ORC_MAX_LAYERS 5
 #define ORC_CHUNK 256      /* rows per dot-product chunk (summation spec) */
 #define ORC_SPMV_LANES 8   /* virtual lanes per CSR row (summation spec)  */
+#define ORC_DOT_GROUP 64   /* chunks per group in the two-level dot combine (problems with more than 256 chunks) */
 
 /* ---- a1: neighbour table (neighbor_lists_gpu.cu:55-78,257-290) ------------------ */
 /* rows [row_start,row_start+row_count) ; out is row_count*nn, -1 padded, ascending j,

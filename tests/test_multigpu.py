@@ -84,13 +84,53 @@ def test_sharding_logic_gloo_world2(tmp_path):
     assert os.path.exists(tmp_path / "ok0") and os.path.exists(tmp_path / "ok1")
 
 
-def test_partition_aligned_matches_reference_arithmetic_on_chunks(kmc):
-    for n, P in ((36498, 2), (36498, 8), (2335872, 8), (9344000, 4), (700, 4)):
+def test_partition_aligned_matches_reference_arithmetic_on_granules(kmc):
+    """rank boundaries on the dot granule (one 256-row chunk up to 256 chunks, one 64-chunk group = 16 384 rows above):
+    the reference's partition arithmetic (KMC_comm.h:249-263) applied to granules"""
+    mg = importlib.import_module(PKG + ".multigpu")
+    for n, P in ((36498, 2), (36498, 8), (2335872, 8), (9344000, 4), (700, 4), (65536, 4), (65537, 4)):
         c, d = kmc.partition(n, P, aligned=True)
-        nch = (n + 255) // 256
-        cc, _ = kmc.partition(nch, P)       # KMC_comm.h:249-263 applied to 256-row chunks
-        assert c.sum() == n
-        assert [int(v) for v in (c + 255) // 256] == [int(v) for v in cc] or c[-1] == 0
+        gran = mg.dot_granule(n)
+        assert gran == (256 if (n + 255) // 256 <= 256 else 16384)
+        ng = (n + gran - 1) // gran
+        cc, _ = kmc.partition(ng, P)
+        assert c.sum() == n and ((d % gran == 0) | (d == n)).all()
+        assert [int(v) for v in (c + gran - 1) // gran] == [int(v) for v in cc] or c[-1] == 0
+
+
+def test_two_level_dot_is_independent_of_the_rank_count(kmc, orc):
+    """summation spec 4.2: chunk partials -> groups of 64 chunks -> final reduce.  Emulates what the ranks exchange (only
+    the group totals of their own rows) for 1, 2, 4 and 8 ranks: every split reproduces the oracle's dot bit for bit."""
+    import ctypes as C
+    rng = np.random.default_rng(11)
+    n = 300 * 256 + 77                       # 301 chunks > 256 -> two-level combine, 5 groups
+    u = rng.standard_normal(n) * 10.0 ** rng.integers(-6, 6, n)
+    v = rng.standard_normal(n)
+    want = orc.dot(u, v)
+    nch = (n + 255) // 256
+    partials = np.array([orc.dot(u[c * 256:(c + 1) * 256], v[c * 256:(c + 1) * 256]) for c in range(nch)])  # 1 chunk = its own dot
+    def group_total(p64):
+        pad = np.zeros(256); pad[:len(p64)] = p64
+        ones = np.ones(256)
+        return orc.dot(pad, ones)            # chunk_reduce_256 of the zero-padded partials (products with 1.0 are exact)
+    for P in (1, 2, 4, 8):
+        counts, displs = kmc.partition(n, P, aligned=True)
+        table = []
+        for r in range(P):                   # each rank reduces the groups of ITS chunks and publishes the totals
+            if counts[r] == 0:
+                continue
+            c0, c1 = int(displs[r]) // 256, (int(displs[r]) + int(counts[r]) + 255) // 256
+            assert c0 % 64 == 0 or counts[r] == 0
+            table += [group_total(partials[g:min(g + 64, c1)]) for g in range(c0, c1, 64)]
+        gt = np.array(table)
+        assert len(gt) == (nch + 63) // 64
+        pad = np.zeros(((len(gt) + 255) // 256) * 256); pad[:len(gt)] = gt
+        assert orc.dot(pad, np.ones(len(pad))) == want or len(gt) > 256
+    # and a system of exactly 256 chunks keeps the single-level result (5 nm device: 143 chunks)
+    m = 256 * 256
+    a, b = rng.standard_normal(m), rng.standard_normal(m)
+    parts = np.array([orc.dot(a[c * 256:(c + 1) * 256], b[c * 256:(c + 1) * 256]) for c in range(256)])
+    assert orc.dot(a, b) == orc.dot(parts, np.ones(256))
 
 
 def test_balanced_partition(kmc):
@@ -100,9 +140,15 @@ def test_balanced_partition(kmc):
     for P in (1, 2, 3, 8):
         c, d = mg.balanced_partition(w, P)
         assert c.sum() == len(w) and d[0] == 0 and (np.diff(d) == c[:-1]).all()
-        assert all(int(v) % 256 == 0 for v in d)
+        assert all(int(v) % 256 == 0 for v in d)             # 21 000 rows = 83 chunks: granule = one chunk
         loads = [int(w[d[q]:d[q] + c[q]].sum()) for q in range(P)]
         assert max(loads) <= w.sum() / P + 256 * 54          # within one chunk of the ideal share
+    w2 = rng.integers(5, 54, 200000)                         # 782 chunks: granule = 64 chunks = 16 384 rows
+    for P in (2, 4, 8):
+        c, d = mg.balanced_partition(w2, P)
+        assert c.sum() == len(w2) and all(int(v) % 16384 == 0 for v in d)
+        loads = [int(w2[d[q]:d[q] + c[q]].sum()) for q in range(P)]
+        assert max(loads) <= w2.sum() / P + 16384 * 54
     c, d = mg.balanced_partition(np.ones(100, dtype=np.int64), 4)   # fewer chunks than ranks: trailing ranks are empty
     assert c.sum() == 100 and (c >= 0).all()
 
@@ -131,7 +177,7 @@ def test_brick_order_gives_slab_partitions_with_thin_halos(kmc, orc):
     peers_b, sent_b = stats["brick"]
     peers_f, sent_f = stats["file"]
     assert max(peers_b) <= 2 and peers_b[0] == 1 and peers_b[-1] == 1, stats
-    assert max(sent_b) < 0.25, stats
+    assert max(sent_b) < 0.30, stats   # (146 k rows = 9 granules of 16 384 rows over 4 ranks: a coarse partition)
     assert max(peers_f) == P - 1 and max(sent_f) > max(sent_b), stats
 
 
