@@ -114,6 +114,7 @@ def use_all_host_threads():
     except AttributeError:
         n = os.cpu_count() or 1
     os.environ["OMP_NUM_THREADS"] = str(n)
+    return n
 
 
 # ------------------------------------------------------------------------------------------------
@@ -124,9 +125,10 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    use_all_host_threads()
+    nthreads = use_all_host_threads()
     from oracle import binding as orc
     from oracle import workload
+    orc.lib().orc_set_num_threads(nthreads)
     w, desc = workload.build(args.workload)
     t0 = time.perf_counter()
     sim = orc.OracleSim(w, use_cells=True)
@@ -163,8 +165,9 @@ def run_reference(args):
 def parity_first_superstep(s, sim, first, world):
     """CHECKER (outside every timed region): the GPU path's first superstep against the CPU oracle on the same inputs.
     `first` holds what the GPU produced in superstep 1.  Returns (report, OracleSim)."""
-    use_all_host_threads()
+    nthreads = use_all_host_threads()
     from oracle import binding as orc
+    orc.lib().orc_set_num_threads(nthreads)   # (an OpenMP runtime loaded earlier -- torch's -- has already read the env)
     t0 = time.perf_counter()
     osim = orc.OracleSim(s, use_cells=True)
     r = osim.superstep(max_log=1 << 16)

@@ -368,6 +368,15 @@ inline double now_s() {
 
 extern "C" {
 
+// (torchrun exports OMP_NUM_THREADS=1 before the process starts; the CPU arm asks for all the cores it may use)
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -161,6 +161,7 @@ void orc_superstep(const orc_params *p, const double *x, const double *y, const 
                    double *pot_total, void *rng, int max_log, int *log_out, orc_step_info *info);
 
 int orc_num_threads(void);
+void orc_set_num_threads(int n);
 
 #ifdef __cplusplus
 }
