@@ -140,6 +140,7 @@ SIGNATURES = {
     "kmcb200_pcg_jacobi_split_sparse": (_i, [_vp, _vp, _vp, _vp, _d, _i, _pi]),
     "kmcb200_imacro": (_i, [_vp, _vp, _vp, _d, _pd]),
     "kmcb200_update_power_sparse": (_i, [_vp, _vp, _vp, _vp, _vp, _pi, _i, _d, _d, _d, _d, _d, _d, _d, _vp, _pd, _pi]),
+    "kmcb200_update_temperature_global": (_i, [_vp, _vp, _vp, _i, _d, _d, _d, _d, _d]),
     "kmcb200_parse_parameters": (_i, [C.c_char_p, C.POINTER(Params)]),
     "kmcb200_parse_parameter_vector": (_i, [C.c_char_p, _i, _i, _pd]),
     "kmcb200_xyz_count": (_i, [C.c_char_p]),
@@ -480,6 +481,11 @@ class Context:
                                                     C.byref(it)))
         T.refresh()
         return im.value, it.value
+
+    # -- f-4
+    def update_temperature_global(self, site_power, T_bg, a_coeff, b_coeff, number_steps, C_thermal, small_step):
+        _check(self.lib.kmcb200_update_temperature_global(self.h, _ptr(site_power), _ptr(T_bg), site_power.numel(), a_coeff,
+                                                          b_coeff, number_steps, C_thermal, small_step))
 
     # -- a10
     def events_create(self, neigh):

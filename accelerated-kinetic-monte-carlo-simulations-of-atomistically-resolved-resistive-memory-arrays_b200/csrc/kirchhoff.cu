@@ -687,3 +687,34 @@ extern "C" int kmcb200_update_CB_edge(kmcb200_ctx *ctx, kmcb200_kmat *K, int N, 
     if (iterations_host) *iterations_host = counter;
     return 0;
 }
+
+
+// ---- f-4: global-temperature recurrence.  Replaces update_temperatureglobal_gpu (src/gpu_solvers.h:229-233,
+// src/heat_solver_gpu.cu:43-69): P_tot = sum of site_power (the reference's tree + atomicAdd order is unspecified: summed
+// with the dot-product association of the summation spec), then one scalar update of T_bg (a device scalar, in place).
+namespace {
+__global__ void fill_kernel(double *v, long long n, double a) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = a;
+}
+}  // namespace
+extern "C" int kmcb200_update_temperature_global(kmcb200_ctx *ctx, const double *site_power, double *T_bg_dev, int N,
+                                                 double a_coeff, double b_coeff, double number_steps, double C_thermal,
+                                                 double small_step) {
+    KMC_CHECK_ARG(ctx && site_power && T_bg_dev && N > 0, "arguments");
+    double *ones = nullptr;
+    KMC_TRY(kmc_scratch(ctx, 3, (size_t)N * sizeof(double), (void **)&ones));
+    kmc_count_launch();
+    fill_kernel<<<grid1(N), 256, 0, ctx->stream>>>(ones, N, 1.0);
+    KMC_CUDA(cudaGetLastError());
+    double P_tot = 0.0, T = 0.0;
+    KMC_TRY(kmcb200_dot(ctx, site_power, ones, N, &P_tot));
+    KMC_CUDA(cudaMemcpyAsync(&T, T_bg_dev, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    KMC_CUDA(cudaStreamSynchronize(ctx->stream));
+    const double c_coeff = b_coeff + P_tot / C_thermal * small_step;  // update_temp_global (:43-50)
+    const int step = (int)number_steps;
+    T = c_coeff * (1.0 - pow(a_coeff, (double)step)) / (1.0 - a_coeff) + pow(a_coeff, (double)step) * T;
+    KMC_CUDA(cudaMemcpyAsync(T_bg_dev, &T, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    KMC_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}

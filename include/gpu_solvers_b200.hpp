@@ -10,7 +10,7 @@
 //   :54  initialize_sparsity_CB    :57  initialize_sparsity_T      :143-146 update_CB_edge_gpu_sparse
 //   :149-153 update_charge_gpu     :162-164 background_potential_gpu_sparse    :173-178 poisson_gridless_gpu
 //   :181 sum_and_gather_potential  :212-218 update_power_gpu_sparse_dist       :250-260 execute_kmc_step_mpi
-//   :262 copytoConstMemory
+//   :262 copytoConstMemory         :229-233 update_temperatureglobal_gpu
 //   dist_iterative/dist_conjugate_gradient.h:33-47  iterative_solver::conjugate_gradient_jacobi<spmv>
 //   dist_iterative/dist_spmv.h:22-27                dspmv::gpu_packing_cam
 //   src/gpu_buffers.h:12-162 GPUBuffers   src/KMC_comm.h:4-391 KMC_comm   src/random_num.h:4-26 RandomNumberGenerator
@@ -503,6 +503,14 @@ inline void update_power_gpu_sparse_dist(hipblasHandle_t handle, hipsolverDnHand
     KMCB200_CHECK(kmcb200_update_power_sparse(kmcb200::ctx(), r.tmat, (const int *)gpubuf.site_element, gpubuf.site_charge,
                                               gpubuf.site_CB_edge, r.metals_h.data(), num_metals, Vd, high_G, low_G, loop_G,
                                               G0, m_e, V0, gpubuf.atom_virtual_potentials, imacro, &r.last_T_iterations));
+}
+
+// src/gpu_solvers.h:229-233 (heat_solver_gpu.cu:43-69)
+inline void update_temperatureglobal_gpu(const double *site_power, double *T_bg, const int N, const double a_coeff,
+                                         const double b_coeff, const double number_steps, const double C_thermal,
+                                         const double small_step) {
+    KMCB200_CHECK(kmcb200_update_temperature_global(kmcb200::ctx(), site_power, T_bg, N, a_coeff, b_coeff, number_steps,
+                                                    C_thermal, small_step));
 }
 
 // ---- dist_iterative solver layer ------------------------------------------------------------------------------------

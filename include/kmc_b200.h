@@ -292,6 +292,13 @@ int kmcb200_update_power_sparse(kmcb200_ctx *ctx, kmcb200_tmat *tmat, const int 
                                 double high_G, double low_G, double loop_G, double G0, double m_e, double V0,
                                 double *atom_virtual_potentials, double *imacro_host, int *iterations_host);
 
+/* f-4.  Replaces update_temperatureglobal_gpu (src/gpu_solvers.h:229-233, src/heat_solver_gpu.cu:43-69): global
+ * temperature recurrence T_bg <- c (1 - a^steps) / (1 - a) + a^steps T_bg with c = b + sum(site_power) / C_thermal *
+ * small_step.  T_bg_dev: device scalar, updated in place (host sync). */
+int kmcb200_update_temperature_global(kmcb200_ctx *ctx, const double *site_power, double *T_bg_dev, int N,
+                                      double a_coeff, double b_coeff, double number_steps, double C_thermal,
+                                      double small_step);
+
 /* ------------------------------------------------------------------------------------------------
  * Host model (no GPU needed): the pieces of the reference's host side that feed the path and must be
  * read UNCHANGED: parameters.txt grammar (src/input_parser.cpp:3-399), xyz files (src/utils.cpp:72-98),

@@ -471,4 +471,14 @@ int orc_update_CB_edge(int N, int N_left, int N_right, const int *element, const
     return counter;
 }
 
+// f-4: update_temperatureglobal_gpu (heat_solver_gpu.cu:43-69): returns the new T_bg
+double orc_update_temperature_global(const double *site_power, int N, double T_bg, double a_coeff, double b_coeff,
+                                     double number_steps, double C_thermal, double small_step) {
+    std::vector<double> ones((size_t)N, 1.0);
+    double P_tot = orc_dot(site_power, ones.data(), N);
+    double c_coeff = b_coeff + P_tot / C_thermal * small_step;
+    int step = (int)number_steps;
+    return c_coeff * (1.0 - std::pow(a_coeff, (double)step)) / (1.0 - a_coeff) + std::pow(a_coeff, (double)step) * T_bg;
+}
+
 }  // extern "C"

@@ -99,3 +99,21 @@ def test_chain_after_kmc_events(kmc, ctx, orc, s5):
     h = T.to_host()
     assert (h["tunnel_atoms"] == ko.tunnel_atoms).all() and (h["t_col"] == ko.t_col).all() and (h["val"] == ko.data).all()
     T.close()
+
+
+def test_global_temperature_recurrence(ctx, orc):
+    """f-4: update_temperatureglobal_gpu (heat_solver_gpu.cu:43-69): exact sum of the site powers (summation spec) and the
+    scalar recurrence; several calls chained like a bias sweep with heating"""
+    import ctypes as C
+    L = orc.lib(); L.orc_update_temperature_global.restype = C.c_double
+    rng = np.random.default_rng(3)
+    for N in (1, 300, 37650, 100003):
+        power = np.abs(rng.standard_normal(N)) * 1e-9
+        T_dev = ctx.dev_d(np.array([300.0]))
+        T = 300.0
+        for step in range(3):
+            a, b, steps, Cth, small = 0.99, 3.0 + step, 50.0, 1e-15, 1e-16
+            ctx.update_temperature_global(ctx.dev_d(power), T_dev, a, b, steps, Cth, small)
+            T = L.orc_update_temperature_global(orc._p(power), C.c_int(N), C.c_double(T), C.c_double(a), C.c_double(b),
+                                                C.c_double(steps), C.c_double(Cth), C.c_double(small))
+            assert to_np(T_dev)[0] == T

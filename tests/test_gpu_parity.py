@@ -387,6 +387,50 @@ def test_cpp_host_driver_runs_the_current_solver(kmc, orc, s5, tmp_path):
     assert np.allclose(mine, gold[:2], rtol=1e-3)
 
 
+def test_cpp_host_driver_bias_sweep(kmc, ctx, s5, tmp_path):
+    """f-4: the bias loop over the V_switch / t_switch vectors (src/kmc_main.cpp:255-575): two bias points; the second
+    starts from the structure the first one left, the warm PCG start and the KMC generator carry over.  The C++ host's
+    'KMC time is:' lines against the Python mirror of the same loop (same library, independent host code)."""
+    import shutil, subprocess
+    exe = os.path.join(os.path.dirname(kmc.LIB_PATH), "kmc_b200_run")
+    if not os.path.exists(exe):
+        pytest.skip("kmc_b200_run not built")
+    src = os.path.join(GOLD, "5nm_device")
+    lines = open(os.path.join(src, "parameters.txt")).read().split("\n")
+    out = []
+    for l in lines:
+        if l.startswith("V_switch"):
+            l = "V_switch = 5 6 // two bias points"
+        if l.startswith("t_switch"):
+            l = "t_switch = 6e-14 8e-14 // [s]"
+        out.append(l)
+    open(tmp_path / "parameters.txt", "w").write("\n".join(out))
+    shutil.copy(os.path.join(src, "reordered_device_5.xyz"), tmp_path / "reordered_device_5.xyz")
+    r = subprocess.run([exe, str(tmp_path / "parameters.txt")], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    txt = open(tmp_path / "output1_0.txt").read()
+    assert "Applied Voltage = 5 V" in txt and "Applied Voltage = 6 V" in txt
+    mine = [float(l.split(":")[1]) for l in txt.split("\n") if l.startswith("KMC time is")]
+    # Python mirror of the bias loop
+    dev = kmc.DeviceKMC(s5, ctx=ctx)
+    want = []
+    for Vd, t in ((5.0, 6e-14), (6.0, 8e-14)):
+        dev.s.Vd = Vd
+        dev.kmc_time = 0.0
+        while dev.kmc_time < t:
+            dev.superstep()
+            want.append(dev.kmc_time)
+    dev.s.Vd = 5.0
+    assert len(mine) == len(want) >= 3 and np.allclose(mine, want, rtol=2e-5)    # 6 printed digits
+    assert os.path.exists(tmp_path / "Results_5.000000" / "snapshot_init.xyz")
+    snaps6 = sorted(os.listdir(tmp_path / "Results_6.000000"))
+    assert "snapshot_init.xyz" in snaps6 and len(snaps6) == 2
+    end5 = [f for f in os.listdir(tmp_path / "Results_5.000000") if f != "snapshot_init.xyz"][0]
+    a = [l.split()[0] for l in open(tmp_path / "Results_5.000000" / end5).read().split("\n")[2:37652]]
+    b = [l.split()[0] for l in open(tmp_path / "Results_6.000000" / "snapshot_init.xyz").read().split("\n")[2:37652]]
+    assert a == b    # the second bias point starts from the structure the first one left
+
+
 # ---------------------------------------------------------------- edge cases
 def test_edge_empty_ranges_and_bad_arguments(kmc, ctx, s_small):
     s = s_small
