@@ -108,7 +108,13 @@ SIGNATURES = {
     "kmcb200_background_potential": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _pi, _i, _d, _d, _d, _vp, _pi]),
     "kmcb200_sparsity_K_row_counts": (_i, [_vp, _i, _vp, _vp, _vp, _pd, _i, _d, _i, _i, _vp]),
     "kmcb200_comm_create": (_i, [_vp, _i, _i, _i, _pi, _pi, _pvp]),
+    "kmcb200_comm_create_ex": (_i, [_vp, _i, _i, _i, _pi, _pi, _ll, _pvp]),
     "kmcb200_comm_destroy": (_i, [_vp]),
+    "kmcb200_comm_allgather": (_i, [_vp, _vp, _pi, _pi]),
+    "kmcb200_rdv_open": (_i, [C.c_char_p, _i, _i, _pvp]),
+    "kmcb200_rdv_allgather": (_i, [_vp, _vp, C.c_size_t, _vp]),
+    "kmcb200_rdv_barrier": (_i, [_vp]),
+    "kmcb200_rdv_close": (_i, [_vp]),
     "kmcb200_comm_ipc_handle": (_i, [_vp, _vp]),
     "kmcb200_comm_open_peers": (_i, [_vp, _vp]),
     "kmcb200_kmat_attach_comm": (_i, [_vp, _vp]),

@@ -37,6 +37,11 @@ struct CommDev {
     unsigned long long *peer_flag_dot[KMC_MAX_RANKS];   // peer's flag_dot array (we write entry [rank])
     unsigned long long *peer_flag_halo[KMC_MAX_RANKS];
     const unsigned char *send_mask;  // local rows: bit q set -> peer q needs this row's p entry
+    // all-gather of row slices (potentials): the owner stages its slice in its own arena, peers pull it over NVLink
+    double *gather;                                   // local staging region (gather_cap doubles)
+    const double *peer_gather[KMC_MAX_RANKS];
+    unsigned long long *flag_gather, *flag_ack;       // local, [KMC_MAX_RANKS] each, written by peers
+    unsigned long long *peer_flag_gather[KMC_MAX_RANKS], *peer_flag_ack[KMC_MAX_RANKS];
     unsigned long long timeout_ns;   // bound of every peer-flag wait
     int *err;                        // device word raised when a wait timed out (CgState::comm_error of the context)
 };
@@ -49,6 +54,10 @@ struct kmcb200_comm {
     char *arena = nullptr;  // local allocation shared with the peers through CUDA IPC
     size_t arena_bytes = 0;
     size_t off_p[2] = {0, 0}, off_partials = 0, off_gtotals = 0, off_flag_dot = 0, off_flag_halo = 0;
+    size_t off_gather = 0, off_flag_gather = 0, off_flag_ack = 0;
+    long long gather_cap = 0;          // doubles in the all-gather staging region
+    unsigned long long gather_seq = 0;  // host-side call counter (identical on every rank)
+    int *err_word = nullptr;            // device int raised by a timed-out wait outside a PCG solve
     int group_chunks = 0, ngroups_global = 0;
     bool masks_set = false;  // kmcb200_comm_set_send_masks was called (required before any sharded SpMV / PCG)
     char *peer_arena[KMC_MAX_RANKS] = {nullptr};

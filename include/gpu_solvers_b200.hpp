@@ -23,9 +23,14 @@
 // What the reference keeps in __constant__ memory, rocSPARSE descriptors and Distributed_matrix internals lives in
 // library handles (kmcb200_kmat / kmcb200_events / kmcb200_tmat) owned by a per-process runtime record.
 // Errors: the reference's gpuErrchk prints and exit(1)s (src/utils.h:145-154); KMCB200_CHECK does the same.
-// Multi-rank: this header drives ONE rank per process; with size > 1 the row-sharded solve needs the peer-memory bootstrap
-// of kmc_b200.h ("(e) Multi-GPU"), which the Python driver (multigpu.py) provides; the entry points below stop with a clear
-// message instead of computing a wrong answer when called with size > 1.
+// Multi-rank (one process per GPU, like the reference's one MPI rank per GCD): the K solve (row blocks) and the Coulomb sum
+// (site rows) are sharded, charges / rate list / event selection are replicated (every rank draws the same events from the
+// same generator).  The bootstrap (CUDA-IPC handles, halo need maps, barriers) runs over a shared directory named by the
+// environment variable KMCB200_RENDEZVOUS (kmcb200_rdv_*); the per-step exchanges run over NVLink peer memory
+// (kmcb200_comm_allgather, and the halo / dot exchanges inside the PCG kernels).  Rank and size come from the launcher's
+// environment (kmcb200_mpi_compat.h).  Rank boundaries of the K rows are placed on the library's dot granule
+// (kmcb200_partition_aligned) instead of the reference's row-count split, which keeps results bit-identical for every
+// rank count.  The Kirchhoff chain is single-rank.
 #pragma once
 
 #include <cstdio>
@@ -113,6 +118,8 @@ struct Runtime {
     GPUBuffers *gpubuf = nullptr;      // the (single) GPUBuffers of the process: poisson_gridless_gpu needs site_element
     kmcb200_events *events = nullptr;  // event list + device MT19937 (src/kmc_events.cu:356-361 + __constant__ energies)
     kmcb200_tmat *tmat = nullptr;      // T_distributed + tunnel block
+    kmcb200_comm *comm = nullptr;      // row-sharded exchange plan of the K solve (size > 1)
+    kmcb200_rdv *rdv = nullptr;        // bootstrap rendezvous (size > 1)
     std::vector<int> metals_h;
     std::vector<double> E_gen, E_rec, E_Vdiff, E_Odiff;
     int last_cg_iterations = 0, last_n_events = 0, last_T_iterations = 0;
@@ -142,16 +149,32 @@ inline void d2h(T *dst, const T *src, size_t n) { KMCB200_CHECK(kmcb200_memcpy_d
 inline void sync() { KMCB200_CHECK(kmcb200_synchronize(ctx())); }
 inline void single_rank_only(int size, const char *who) {
     if (size > 1) {
-        std::fprintf(stderr, "kmc_b200: %s: this C++ shim drives one rank per process; the row-sharded multi-GPU solve is "
-                             "bootstrapped through kmcb200_comm_* (see kmc_b200.h section (e) and multigpu.py)\n", who);
+        std::fprintf(stderr, "kmc_b200: %s is a single-rank call in this build\n", who);
         std::exit(1);
     }
+}
+// bootstrap rendezvous of the node's ranks (opened on first use)
+inline kmcb200_rdv *rdv(int rank, int size) {
+    Runtime &r = rt();
+    if (!r.rdv) {
+        const char *dir = std::getenv("KMCB200_RENDEZVOUS");
+        if (!dir) {
+            std::fprintf(stderr, "kmc_b200: %d ranks need KMCB200_RENDEZVOUS=<directory shared by the ranks> for the bootstrap\n", size);
+            std::exit(1);
+        }
+        KMCB200_CHECK(kmcb200_rdv_open(dir, rank, size, &r.rdv));
+    }
+    return r.rdv;
 }
 }  // namespace kmcb200
 
 inline int hipDeviceSynchronize() { kmcb200::sync(); return 0; }
 #ifndef KMCB200_HAVE_MPI
-inline int kmcb200_host_barrier(MPI_Comm c) { kmcb200::single_rank_only(c ? c->size : 1, "MPI_Barrier"); return 0; }
+inline int kmcb200_host_barrier(MPI_Comm c) {
+    kmcb200::sync();
+    KMCB200_CHECK(kmcb200_rdv_barrier(kmcb200::rdv(c->rank, c->size)));
+    return 0;
+}
 #endif
 
 // ---- dist_iterative/dist_objects.h: the two objects the callers hold ---------------------------------------------------
@@ -221,6 +244,7 @@ public:
             kmcb200_partition(n, size_global, c, d);
         };
         part(nrows_K, counts_K, displs_K);
+        if (size_global > 1) kmcb200_partition_aligned(nrows_K, size_global, counts_K, displs_K);  // dot-granule boundaries
         part(nrows_T, counts_T, displs_T);
         part(nrows_pairwise, counts_pairwise, displs_pairwise);
         part(nrows_events, counts_events, displs_events);
@@ -358,17 +382,46 @@ inline void compute_cutoff_list(MPI_Comm &pairwise_comm, int *counts, int *displ
 // src/gpu_solvers.h:53
 inline void initialize_sparsity_K(GPUBuffers &gpubuf, int pbc, const double nn_dist, int num_atoms_contact,
                                   KMC_comm &kmc_comm) {
-    kmcb200::single_rank_only(kmc_comm.size_K, "initialize_sparsity_K");
-    const int r = kmc_comm.rank_K;
+    using namespace kmcb200;
+    const int r = kmc_comm.rank_K, size = kmc_comm.size_K;
+    const int n = gpubuf.N_ - 2 * num_atoms_contact;
+    Runtime &R = rt();
+    if (size > 1) {
+        // exchange plan over NVLink peer memory: arena + CUDA-IPC handles exchanged through the rendezvous directory
+        long long cap = 0;
+        for (int q = 0; q < size; ++q) {
+            if (kmc_comm.counts_K[q] > cap) cap = kmc_comm.counts_K[q];
+            if (kmc_comm.counts_pairwise[q] > cap) cap = kmc_comm.counts_pairwise[q];
+        }
+        KMCB200_CHECK(kmcb200_comm_create_ex(ctx(), r, size, n, kmc_comm.counts_K, kmc_comm.displs_K, cap, &R.comm));
+        std::vector<unsigned char> mine(64), all((size_t)64 * size);
+        KMCB200_CHECK(kmcb200_comm_ipc_handle(R.comm, mine.data()));
+        KMCB200_CHECK(kmcb200_rdv_allgather(rdv(r, size), mine.data(), 64, all.data()));
+        KMCB200_CHECK(kmcb200_comm_open_peers(R.comm, all.data()));
+    }
     kmcb200_kmat *K = nullptr;
-    KMCB200_CHECK(kmcb200_initialize_sparsity_K(kmcb200::ctx(), gpubuf.N_, gpubuf.site_x, gpubuf.site_y, gpubuf.site_z,
+    KMCB200_CHECK(kmcb200_initialize_sparsity_K(ctx(), gpubuf.N_, gpubuf.site_x, gpubuf.site_y, gpubuf.site_z,
                                                 gpubuf.lattice_host, pbc, nn_dist, num_atoms_contact, num_atoms_contact,
                                                 kmc_comm.displs_K[r], kmc_comm.counts_K[r], &K));
-    gpubuf.K_distributed = new Distributed_matrix(K, gpubuf.N_ - 2 * num_atoms_contact, kmc_comm.counts_K, kmc_comm.displs_K,
-                                                  kmc_comm.comm_K);
+    if (size > 1) {
+        KMCB200_CHECK(kmcb200_kmat_attach_comm(K, R.comm));
+        // halo need maps: which rows of the other ranks does my block reference (all-gathered out of band, once)
+        unsigned char *need_d = dmalloc<unsigned char>((size_t)n), *all_d = dmalloc<unsigned char>((size_t)n * size);
+        std::vector<unsigned char> need_h((size_t)n), all_h((size_t)n * size);
+        KMCB200_CHECK(kmcb200_kmat_need_map(K, need_d));
+        d2h(need_h.data(), need_d, (size_t)n);
+        sync();
+        KMCB200_CHECK(kmcb200_rdv_allgather(rdv(r, size), need_h.data(), (size_t)n, all_h.data()));
+        h2d(all_d, all_h.data(), (size_t)n * size);
+        KMCB200_CHECK(kmcb200_comm_set_send_masks(R.comm, all_d));
+        sync();
+        kmcb200_free(ctx(), need_d);
+        kmcb200_free(ctx(), all_d);
+        KMCB200_CHECK(kmcb200_rdv_barrier(rdv(r, size)));  // every rank's masks are in place before the first exchange
+    }
+    gpubuf.K_distributed = new Distributed_matrix(K, n, kmc_comm.counts_K, kmc_comm.displs_K, kmc_comm.comm_K);
     int self = r;
-    gpubuf.K_p_distributed = new Distributed_vector(gpubuf.N_ - 2 * num_atoms_contact, kmc_comm.counts_K, kmc_comm.displs_K, 1,
-                                                    &self, kmc_comm.comm_K);
+    gpubuf.K_p_distributed = new Distributed_vector(n, kmc_comm.counts_K, kmc_comm.displs_K, 1, &self, kmc_comm.comm_K);
 }
 // src/gpu_solvers.h:54: the CB-edge solve reuses the K sparsity here
 inline void initialize_sparsity_CB(GPUBuffers &, int, const double, int) {}
@@ -395,6 +448,11 @@ inline void background_potential_gpu_sparse(hipblasHandle_t handle_cublas, hipso
                                                (const int *)gpubuf.site_element, gpubuf.site_charge, r.metals_h.data(),
                                                num_metals, d_Vd, d_high_G, d_low_G, gpubuf.site_potential_boundary,
                                                &r.last_cg_iterations));
+    // every rank needs the whole boundary potential (rate list and events are replicated): NVLink all-gather of the row
+    // blocks instead of the reference's MPI_Gatherv to the root (src/kmc_main.cpp:367-384) + later MPI_Bcast
+    if (r.comm)
+        KMCB200_CHECK(kmcb200_comm_allgather(r.comm, gpubuf.site_potential_boundary + N_left_tot,
+                                             gpubuf.K_distributed->counts, gpubuf.K_distributed->displacements));
 }
 // src/gpu_solvers.h:173-178.  sigma / k / lattice are DEVICE pointers (src/gpu_buffers.h:130-134).  The membership test of
 // the reference's cutoff list (element in {d, Od, V, O}, src/neighbor_lists_gpu.cu:96,123) is evaluated inline from the
@@ -415,7 +473,10 @@ inline void poisson_gridless_gpu(const int num_atoms_contact, const int pbc, con
 // src/gpu_solvers.h:181
 inline void sum_and_gather_potential(GPUBuffers &gpubuf, int num_atoms_first_layer, KMC_comm &kmc_comm) {
     (void)num_atoms_first_layer;
-    kmcb200::single_rank_only(kmc_comm.size_K, "sum_and_gather_potential");
+    kmcb200::Runtime &r = kmcb200::rt();
+    if (r.comm)  // the Coulomb potentials of the other ranks' site rows (src/kmc_main.cpp:411-427 + potential_solver_gpu.cu:1133-1142)
+        KMCB200_CHECK(kmcb200_comm_allgather(r.comm, gpubuf.site_potential_charge, kmc_comm.counts_pairwise,
+                                             kmc_comm.displs_pairwise));
     KMCB200_CHECK(kmcb200_sum_potential(kmcb200::ctx(), gpubuf.N_, gpubuf.site_potential_charge,
                                         gpubuf.site_potential_boundary));
 }

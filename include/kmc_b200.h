@@ -185,7 +185,22 @@ int kmcb200_sparsity_K_row_counts(kmcb200_ctx *ctx, int N, const double *x, cons
                                   int *row_nnz_dev);
 int kmcb200_comm_create(kmcb200_ctx *ctx, int rank, int size, int n_global_rows, const int *counts_host,
                         const int *displs_host, kmcb200_comm **comm_out);
+/* same, with a staging region of gather_capacity doubles for kmcb200_comm_allgather (>= the largest slice this rank
+ * will contribute) */
+int kmcb200_comm_create_ex(kmcb200_ctx *ctx, int rank, int size, int n_global_rows, const int *counts_host,
+                           const int *displs_host, long long gather_capacity, kmcb200_comm **comm_out);
 int kmcb200_comm_destroy(kmcb200_comm *comm);
+/* In-place all-gather of row slices of a device vector over NVLink peer memory: on entry vec[displs[rank] ..
+ * + counts[rank]) is this rank's slice, on return every rank holds all slices.  Replaces the MPI_Gatherv + MPI_Bcast of
+ * the potentials (src/kmc_main.cpp:367-384,411-427, src/potential_solver_gpu.cu:1133-1142).  Host sync. */
+int kmcb200_comm_allgather(kmcb200_comm *comm, double *vec_dev, const int *counts_host, const int *displs_host);
+/* Out-of-band rendezvous of the ranks of ONE node through a shared directory (bootstrap: IPC handles, need maps,
+ * barriers) for hosts without MPI / torch.distributed.  allgather: `all` receives size * bytes. */
+typedef struct kmcb200_rdv kmcb200_rdv;
+int kmcb200_rdv_open(const char *dir, int rank, int size, kmcb200_rdv **rdv_out);
+int kmcb200_rdv_allgather(kmcb200_rdv *rdv, const void *mine_host, size_t bytes, void *all_host);
+int kmcb200_rdv_barrier(kmcb200_rdv *rdv);
+int kmcb200_rdv_close(kmcb200_rdv *rdv);
 int kmcb200_comm_ipc_handle(kmcb200_comm *comm, void *handle64_host);
 int kmcb200_comm_open_peers(kmcb200_comm *comm, const void *handles_host /* size * 64 bytes */);
 int kmcb200_kmat_attach_comm(kmcb200_kmat *kmat, kmcb200_comm *comm);

@@ -431,6 +431,55 @@ def test_cpp_host_driver_bias_sweep(kmc, ctx, s5, tmp_path):
     assert a == b    # the second bias point starts from the structure the first one left
 
 
+def test_cpp_host_driver_two_ranks(kmc, tmp_path):
+    """The compiled host at N > 1 (VERDICT r1 missing #3): two processes of kmc_b200_run -- one rank per process, bootstrap
+    (CUDA-IPC handles, halo need maps, barriers) over a shared directory (kmcb200_rdv_*), K solve row-sharded with halo /
+    dot exchanges in peer memory, Coulomb rows sharded, potentials all-gathered over peer memory, events replicated.
+    Both ranks must log the golden run's KMC times and rank 0 must write the golden final structure.  Uses two GPUs when
+    the box has them, else both ranks share GPU 0 (CUDA IPC works between processes on one device; slower, same code)."""
+    import subprocess
+    import torch
+    exe = os.path.join(os.path.dirname(kmc.LIB_PATH), "kmc_b200_run")
+    if not os.path.exists(exe):
+        pytest.skip("kmc_b200_run not built")
+    ngpu = torch.cuda.device_count()
+    rdv = tmp_path / "rdv"
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, KMCB200_RANK=str(r), KMCB200_WORLD_SIZE="2", KMCB200_RENDEZVOUS=str(rdv),
+                   KMCB200_DEVICE=str(r if ngpu >= 2 else 0), KMCB200_COMM_TIMEOUT_MS="120000")
+        procs.append(subprocess.Popen([exe, os.path.join(GOLD, "5nm_device", "parameters.txt")], cwd=tmp_path, env=env,
+                                      stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    outs = [p.communicate(timeout=900) for p in procs]
+    for p, (so, se) in zip(procs, outs):
+        assert p.returncode == 0, se[-2000:]
+    gold = [float(l.split(":")[1]) for l in open(os.path.join(GOLD, "5nm_device", "output1_0.txt")) if l.startswith("KMC time is")]
+    times = []
+    for r in range(2):
+        out = open(tmp_path / f"output2_{r}.txt").read()
+        times.append([l for l in out.split("\n") if l.startswith("KMC time is")])
+        mine = [float(l.split(":")[1]) for l in times[-1]]
+        assert len(mine) == 6 and np.allclose(mine, gold, rtol=1e-3)
+        times[-1] += [l for l in out.split("\n") if l.startswith("PCG iterations")]
+    assert times[0] == times[1]                      # replicated event selection: identical trajectories
+    # ... and identical to the single-rank run of the same binary: same PCG iteration counts (cold solve included), same
+    # printed KMC times
+    one = tmp_path / "one"
+    os.makedirs(one)
+    r1 = subprocess.run([exe, os.path.join(GOLD, "5nm_device", "parameters.txt")], cwd=one, capture_output=True, text=True,
+                        timeout=600)
+    assert r1.returncode == 0, r1.stderr[-2000:]
+    out1 = open(one / "output1_0.txt").read().split("\n")
+    ref = [l for l in out1 if l.startswith("KMC time is")] + [l for l in out1 if l.startswith("PCG iterations")]
+    assert times[0] == ref and int(ref[6].split(":")[1]) > 100
+    snap = open(tmp_path / "Results_5.000000" / "snapshot_6.xyz").read().split("\n")
+    with gzip.open(os.path.join(GOLD, "5nm_device", "snapshot_6.xyz.gz"), "rt") as f:
+        gsnap = f.read().split("\n")
+    assert [l.split()[0] for l in snap[2:37652]] == [l.split()[0] for l in gsnap[2:37652]]
+    pm = np.array([float(l.split()[4]) for l in snap[2:37652]]); pg = np.array([float(l.split()[4]) for l in gsnap[2:37652]])
+    assert np.abs(pm - pg).max() < 5e-4
+
+
 # ---------------------------------------------------------------- edge cases
 def test_edge_empty_ranges_and_bad_arguments(kmc, ctx, s_small):
     s = s_small
