@@ -67,6 +67,7 @@ struct kmcb200_ctx {
     bool cg_done_stale = false;   // a PCG solve ended abnormally: CgState::done may still be set
     // opted-in dynamic shared memory per kernel family (function attributes are per device, a ctx is bound to one)
     size_t smem_cfg_events = 0, smem_cfg_coulomb = 48 * 1024, smem_cfg_staged = 0;
+    bool smem_cfg_plan = false;
     double *partials = nullptr;   // device, 2 * max chunks
     size_t partials_cap = 0;
 };

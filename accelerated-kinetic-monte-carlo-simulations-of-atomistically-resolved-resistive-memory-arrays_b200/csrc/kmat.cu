@@ -104,7 +104,8 @@ int kmc_kmat_finalize(kmcb200_kmat *K) {
         K->owns_comm = true;
     }
     K->plan_max_unique = 0;
-    if (getenv("KMCB200_SPMV_STAGED")) return kmc_build_spmv_plan(K);  // opt-in experiment, see pcg.cu
+    static const bool staged = getenv("KMCB200_SPMV_STAGED") != nullptr;  // opt-in experiment, see pcg.cu
+    if (staged) return kmc_build_spmv_plan(K);
     return 0;
 }
 

@@ -106,11 +106,10 @@ int kmc_build_spmv_plan(kmcb200_kmat *K) {
     KMC_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), ctx->stream));
     KMC_CUDA(cudaMalloc(&K->u_ptr, (size_t)(nchunks + 1) * sizeof(int)));
     KMC_CUDA(cudaMemsetAsync(K->u_ptr, 0, (size_t)(nchunks + 1) * sizeof(int), ctx->stream));
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!ctx->smem_cfg_plan) {  // function attributes are per device: tracked per context, not per process
         KMC_CUDA(cudaFuncSetAttribute(spmv_plan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PLAN_CAP * 4));
         KMC_CUDA(cudaFuncSetAttribute(spmv_plan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PLAN_CAP * 4));
-        attr_set = true;
+        ctx->smem_cfg_plan = true;
     }
     kmc_count_launch();
     spmv_plan_kernel<false><<<nchunks, PT, PLAN_CAP * 4, ctx->stream>>>(K->rows, K->row_ptr, K->col, K->u_ptr, nullptr,

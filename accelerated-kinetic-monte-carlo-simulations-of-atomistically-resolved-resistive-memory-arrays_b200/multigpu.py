@@ -92,15 +92,15 @@ def allgather_slices(dist, local, counts, displs, out):
 class Comm:
     """kmcb200_comm handle: peer-memory exchange plan of one rank"""
 
-    def __init__(self, ctx: Context, rank: int, size: int, n_global: int, counts, displs, dist=None):
+    def __init__(self, ctx: Context, rank: int, size: int, n_global: int, counts, displs, dist=None, gather_capacity=0):
         import torch
         self.ctx, self.rank, self.size = ctx, rank, size
         self.counts = np.ascontiguousarray(counts, dtype=np.int32)
         self.displs = np.ascontiguousarray(displs, dtype=np.int32)
         self.n_global = n_global
         h = C.c_void_p()
-        _check(ctx.lib.kmcb200_comm_create(ctx.h, rank, size, n_global, self.counts.ctypes.data_as(api._pi),
-                                           self.displs.ctypes.data_as(api._pi), C.byref(h)))
+        _check(ctx.lib.kmcb200_comm_create_ex(ctx.h, rank, size, n_global, self.counts.ctypes.data_as(api._pi),
+                                              self.displs.ctypes.data_as(api._pi), int(gather_capacity), C.byref(h)))
         self.h = h
         if size > 1:
             handle = np.zeros(64, dtype=np.uint8)
@@ -125,6 +125,13 @@ class Comm:
             dist.barrier()
         K._comm = self
         return self
+
+    def allgather(self, vec, counts, displs):
+        """in-place all-gather of row slices of a device vector over NVLink peer memory (kmcb200_comm_allgather)"""
+        counts = np.ascontiguousarray(counts, dtype=np.int32)
+        displs = np.ascontiguousarray(displs, dtype=np.int32)
+        _check(self.ctx.lib.kmcb200_comm_allgather(self.h, _ptr(vec), counts.ctypes.data_as(api._pi),
+                                                   displs.ctypes.data_as(api._pi)))
 
     def info(self):
         r, s, m, b = C.c_int(0), C.c_int(0), C.c_uint(0), C.c_longlong(0)
@@ -160,7 +167,8 @@ class DistributedDeviceKMC(DeviceKMC):
         else:
             self.counts_K, self.displs_K = partition(n, world, aligned=True)
         self.counts_N, self.displs_N = partition(s.N, world)
-        self.comm = Comm(c, rank, world, n, self.counts_K, self.displs_K, dist)
+        self.comm = Comm(c, rank, world, n, self.counts_K, self.displs_K, dist,
+                         gather_capacity=int(max(self.counts_K.max(), self.counts_N.max())))
         self.K = c.initialize_sparsity_K(self.x, self.y, self.z, s.lattice, s.pbc, s.nn_dist, s.N_left, s.N_right,
                                          int(self.displs_K[rank]), int(self.counts_K[rank]))
         self.comm.attach(self.K, dist)
@@ -177,13 +185,13 @@ class DistributedDeviceKMC(DeviceKMC):
         c.update_charge(self.element, self.charge, self.neigh, s.metals)          # replicated (no Allgatherv)
         self.last_cg_iterations = c.background_potential(self.K, self.N, s.N_left, s.N_right, self.element, self.charge,
                                                          s.metals, s.Vd, s.high_G, s.low_G, self.pot_boundary)
-        lo = s.N_left + int(self.displs_K[r])
+        # potentials of the other ranks' rows: pulled out of the owners' arenas over NVLink (replaces the reference's
+        # MPI_Gatherv + MPI_Bcast, src/kmc_main.cpp:367-384,411-427, src/potential_solver_gpu.cu:1133-1142)
         interior = self.pot_boundary[s.N_left: self.N - s.N_right]
-        allgather_slices(self.dist, self.pot_boundary[lo: lo + int(self.counts_K[r])].clone(), self.counts_K,
-                         self.displs_K, interior)
+        if self.world > 1:
+            self.comm.allgather(interior, self.counts_K, self.displs_K)
         c.poisson_gridless(self.x, self.y, self.z, self.element, self.charge, s.sigma, s.k, self.pot_charge,
                            row_start=int(self.displs_N[r]), row_count=int(self.counts_N[r]))
-        lo = int(self.displs_N[r])
-        allgather_slices(self.dist, self.pot_charge[lo: lo + int(self.counts_N[r])].clone(), self.counts_N,
-                         self.displs_N, self.pot_charge)
+        if self.world > 1:
+            self.comm.allgather(self.pot_charge, self.counts_N, self.displs_N)
         c.sum_potential(self.pot_charge, self.pot_boundary)

@@ -152,7 +152,10 @@ int kmcb200_assemble_K(kmcb200_ctx *ctx, kmcb200_kmat *kmat, int N, int N_left, 
 int kmcb200_pcg_jacobi(kmcb200_ctx *ctx, kmcb200_kmat *kmat, double *r_local, double *x_local,
                        const double *diag_inv_local, double relative_tolerance, int max_iterations,
                        int *iterations_host);
-/* y = A x (x: this rank's rows; halo handled internally).  dspmv::gpu_packing_cam equivalent. */
+/* y = A x (x: this rank's rows; halo handled internally).  dspmv::gpu_packing_cam equivalent.  Row-sharded use
+ * requires a STRUCTURALLY SYMMETRIC matrix (like the reference's Distributed_matrix, dist_objects.h:66 "assumes that the
+ * matrix is symmetric"): the halo flags that order the reuse of the double-buffered p vector rely on "I send to q <=> I
+ * receive from q".  kmcb200_initialize_sparsity_K matrices are symmetric by construction. */
 int kmcb200_spmv(kmcb200_ctx *ctx, kmcb200_kmat *kmat, const double *x_local, double *y_local);
 /* y = A x and x.(A x) in one pass (the fused SpMV + p.Ap kernel of the PCG iteration); single rank.  dot_host may be
  * NULL (no host sync; the scalar stays on the device). */
