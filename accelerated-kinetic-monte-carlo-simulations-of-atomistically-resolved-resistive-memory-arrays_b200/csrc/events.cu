@@ -94,6 +94,26 @@ __device__ __forceinline__ void warp_scan_256(Scan256 &r) {
     r.excl = __shfl_up_sync(KMC_FULL_MASK, S, 1);
     r.total = __shfl_sync(KMC_FULL_MASK, S, 31);
 }
+// two independent scans with their dependent chains interleaved (the latency of one)
+__device__ __forceinline__ void warp_scan_256x2(Scan256 &r, Scan256 &q) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 1; k < 8; ++k) {
+        r.a[k] = r.a[k - 1] + r.a[k];
+        q.a[k] = q.a[k - 1] + q.a[k];
+    }
+    double S = r.a[7], T = q.a[7];
+#pragma unroll
+    for (int d = 1; d <= 16; d <<= 1) {
+        const double o = __shfl_up_sync(KMC_FULL_MASK, S, d);
+        const double u = __shfl_up_sync(KMC_FULL_MASK, T, d);
+        if (lane >= d) { S = o + S; T = u + T; }
+    }
+    r.excl = __shfl_up_sync(KMC_FULL_MASK, S, 1);
+    q.excl = __shfl_up_sync(KMC_FULL_MASK, T, 1);
+    r.total = __shfl_sync(KMC_FULL_MASK, S, 31);
+    q.total = __shfl_sync(KMC_FULL_MASK, T, 31);
+}
 __device__ __forceinline__ double scan_incl(const Scan256 &r, int k) {
     return ((threadIdx.x & 31) > 0) ? (r.excl + r.a[k]) : r.a[k];
 }
@@ -177,6 +197,22 @@ __device__ __forceinline__ int warp_pick_incl(const double inc[8], double number
     *prev = pv;
     *cur = cv;
     return tsel;
+}
+// max over t < tsel of incl[t] (incl[8 lane + k] held as inc[k]); -inf when tsel == 0.  With it the selection rule
+// "first t whose inclusive prefix exceeds number" can be VALIDATED for a given t without looking at the 256 values again:
+// t is the selected element  <=>  !(max_before > number) && incl[t] > number.
+__device__ __forceinline__ double warp_max_before(const double inc[8], int tsel) {
+    const int lane = threadIdx.x & 31;
+    double m = -1.0 / 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        if (8 * lane + k < tsel && inc[k] > m) m = inc[k];
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const double o = __shfl_xor_sync(KMC_FULL_MASK, m, off);
+        if (o > m) m = o;
+    }
+    return m;
 }
 // butterfly row sum of the summation spec: lane l holds p[l] + p[l+32]
 __device__ __forceinline__ double warp_row_sum(double p0, double p1) { return kmc_warp_xor_sum(p0 + p1); }
@@ -342,6 +378,14 @@ __device__ __forceinline__ double mt_next_double(unsigned *mt, int &pos) {
 #define EV_TICK(k) do { } while (0)
 #endif
 
+// KMC_EV_TRACE: per-warp clock64 stamps at the phase boundaries of 64 consecutive events (diagnostics: who waits for whom)
+#ifdef KMC_EV_TRACE
+#define EV_TRACE_FIRST 2000
+#define EV_TR(k) do { const int te_ = tr_e - EV_TRACE_FIRST + ((k) == 0 || ((k) >= 7 && (k) <= 11) ? 1 : 0); if (lane == 0 && te_ >= 0 && te_ < 64 && a.phase_cycles) a.phase_cycles[(te_ * 16 + warp) * 16 + (k)] = clock64(); } while (0)
+#else
+#define EV_TR(k) do { } while (0)
+#endif
+
 struct EvLoopArgs {
     int N, nn;
     long long nchunk, nsuper;
@@ -401,6 +445,17 @@ struct EvRecord {
     int i, j, ty, slot;
     double psum;
     double pos, w;  // cumulative rate in front of row i and the row's total rate (for the predictor, approximate)
+    int fast;       // the event is the predictor's (validated): its zero-out inputs are already staged in shared memory
+};
+
+// What the predictor publishes about the next event: its path through the hierarchy and, per level, the interval of
+// `number` for which that path is what the exact selection rule picks (see warp_max_before).
+struct EvPrediction {
+    int ts, tc, tr, n;            // super, chunk in super, row in chunk, slot in row
+    int ej, ety;                  // partner site and event type of the slot
+    double lo_c, hi_c, prev_c;    // chunk level: max prefix in front, prefix at tc, prefix at tc - 1 (0 for tc == 0)
+    double lo_r, hi_r, prev_r;    // row level
+    double acc_b, acc_a;          // slot level: running sum before / after the slot (sequential over the non-zero slots)
 };
 
 // The persistent event loop: ONE CTA of 16 warps, three block barriers per event.
@@ -442,7 +497,18 @@ __global__ void __launch_bounds__(EV_THREADS, 1) event_loop_kernel(EvLoopArgs a)
     __shared__ double s_spec_incl[256];         // row prefixes of the predicted chunk, tpos layout
     __shared__ double s_spec_p[64];             // rates of the predicted row
     __shared__ int s_spec_nb[64], s_spec_ty[64];
-    __shared__ int s_spec_chunk, s_spec_r, s_spec_valid;
+    __shared__ int s_spec_chunk, s_spec_r;
+    __shared__ EvPrediction s_pred;
+    // zero-out inputs of the predicted event, double-buffered by event parity (the predictor fills buffer (e+1)&1 while the
+    // zero-out of event e may still read buffer e&1)
+    __shared__ int s_pz_packed[2][2 * REV_STRIDE];   // reverse-index rows of the predicted event's two sites ...
+    __shared__ double s_pz_oldp[2][2 * REV_STRIDE];  // ... and the rates those slots hold
+    __shared__ int s_pz_event[2];                    // index of the event each buffer was staged for
+    __shared__ int s_pred_ok;                        // the prediction reached the slot level
+    __shared__ int s_h_done;                    // = e + 1 once the residence time of event e is stored
+    __shared__ int s_b2_event;                  // = e + 1 once event e passed barrier B2 (its dirty lists are complete)
+    __shared__ int s_pred_clean;                // bit 0: predicted chunk not dirty in this event, bit 1: nor its super
+    __shared__ double s_top_incl[256];          // inclusive prefixes of the super sums as the last selector scanned them
     __shared__ int s_spec_ready;                // = e once the speculation for event e is complete
 
     const int tid = threadIdx.x;
@@ -490,7 +556,7 @@ __global__ void __launch_bounds__(EV_THREADS, 1) event_loop_kernel(EvLoopArgs a)
         n_rows = 0;
         n_chunks = 0;
         n_supers = 0;
-        s_spec_chunk = -1; s_spec_r = -1; s_spec_valid = 0; s_spec_ready = 0;
+        s_spec_chunk = -1; s_spec_r = -1; s_spec_ready = 0; s_h_done = 0; s_b2_event = 0; s_pred_clean = 0; s_pred_ok = 0; s_pz_event[0] = s_pz_event[1] = -1;
     }
     __syncthreads();
     if (tid == 0) {
@@ -502,13 +568,22 @@ __global__ void __launch_bounds__(EV_THREADS, 1) event_loop_kernel(EvLoopArgs a)
     __syncthreads();
 
     bool i_select = (warp == 0);
+#ifdef KMC_EV_TRACE
+    __shared__ long long s_tr_cnt[8];
+    if (tid < 8) s_tr_cnt[tid] = 0;
+    int tr_e = -1;  // index of the event whose phases are being stamped (set after barrier A)
+#endif
     while (true) {
         // =============================== S: selector (one warp, warp-synchronous) =============================
+        EV_TR(0);
         if (i_select) {
             const int e = s_nevents;  // index of the event selected now
+            while (*(volatile int *)&s_h_done < e) { }  // residence time of event e - 1
+            __threadfence_block();
             const bool go = (s_event_time < a.inv_freq_threshold) && (a.max_events <= 0 || e < a.max_events);
             int ei = -1, ej = -1, ety = KMCB200_NULL_EVENT, eslot = -1;
             double Psum = 0.0, pos = 0.0, wrow = 0.0;
+            int fast_rec = 0;
             if (go) {
                 // ---- top level: scan_256 over the super sums (shared memory) ------------------------------
                 Scan256 sc;
@@ -522,9 +597,56 @@ __global__ void __launch_bounds__(EV_THREADS, 1) event_loop_kernel(EvLoopArgs a)
                 double number = u1 * Psum;
                 double prev, cur;
                 int ts = (Psum > 0.0) ? warp_pick_256(sc, v, number, &prev) : -1;
+                if (a.use_spec) {  // for the predictor of this event (the super sums do not change before its repair)
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) s_top_incl[32 * k + lane] = scan_incl(sc, k);
+                }
+                EV_TR(8);
                 int r = -1;  // all slot indices fit 32 bits: N * nn <= 16.7 M * 64 < 2^31
                 bool spec = false;
-                if (ts >= 0) {
+                // ---- fast path: the predictor's path, VALIDATED level by level against the exact `number` (the intervals
+                // come from arrays no event has touched since the predictor read them: chunk prefixes of a super that was
+                // not re-scanned, row prefixes / rates of a chunk that is not dirty).  Every check is exactly the selection
+                // rule applied to that element, so an accepted path is the path the full selection below would take.
+                bool fast = false, chunk_clean = false;
+                int pc = -1;
+                if (ts >= 0 && a.use_spec) {
+                    while (*(volatile int *)&s_spec_ready < e) { }
+                    __threadfence_block();
+                    EV_TR(9);
+                    pc = *(volatile int *)&s_spec_chunk;
+                    const int clean = *(volatile int *)&s_pred_clean;  // the predictor's verdict on the dirty lists
+                    chunk_clean = (clean & 1) != 0;
+                    const bool super_clean = (clean & 2) != 0;
+                    if (*(volatile int *)&s_pred_ok && super_clean && s_pred.ts == ts) {
+                        const double n1 = number - prev;
+                        const double n2 = n1 - s_pred.prev_c;
+                        const double n3 = n2 - s_pred.prev_r;
+                        if (!(s_pred.lo_c > n1) && s_pred.hi_c > n1 && !(s_pred.lo_r > n2) && s_pred.hi_r > n2 &&
+                            !(s_pred.acc_b > n3) && s_pred.acc_a > n3) {
+                            fast = true;
+                            fast_rec = 1;
+                            pos = (prev + s_pred.prev_c) + s_pred.prev_r;
+                            wrow = s_pred.hi_r - s_pred.prev_r;
+                            ei = (ts * 256 + s_pred.tc) * 256 + s_pred.tr;
+                            ej = s_pred.ej; ety = s_pred.ety;
+                            eslot = ei * nn + s_pred.n;
+#ifdef KMC_EV_TRACE
+                            if (lane == 0) s_tr_cnt[0]++;
+#endif
+                        }
+                    }
+#ifdef KMC_EV_TRACE
+                    if (lane == 0) {
+                        s_tr_cnt[1] += (s_pred_ok != 0);
+                        s_tr_cnt[2] += super_clean;
+                        s_tr_cnt[3] += chunk_clean;
+                        s_tr_cnt[4] += (s_pred.ts == ts);
+                    }
+#endif
+                }
+                EV_TR(10);
+                if (ts >= 0 && !fast) {
                     number = number - prev;
                     pos = prev;
                     // ---- chunk level: stored prefixes of super ts ---------------------------------------------
@@ -540,11 +662,7 @@ __global__ void __launch_bounds__(EV_THREADS, 1) event_loop_kernel(EvLoopArgs a)
                         pos = pos + prev;
                         const int chunk = ts * 256 + tc;
                         // ---- row level: stored prefixes of the chunk: the predictor's copy, else one round trip ------
-                        if (a.use_spec) {
-                            while (*(volatile int *)&s_spec_ready < e) { }
-                            __threadfence_block();
-                            spec = (*(volatile int *)&s_spec_valid != 0) && (*(volatile int *)&s_spec_chunk == chunk);
-                        }
+                        spec = chunk_clean && (pc == chunk);  // the predictor's copy of this chunk's row prefixes
                         const int rbase = chunk * 256 + 8 * lane;
                         if (spec) {
 #pragma unroll
@@ -611,169 +729,198 @@ __global__ void __launch_bounds__(EV_THREADS, 1) event_loop_kernel(EvLoopArgs a)
                     }
                 }
             }
+            EV_TR(11);
             if (lane == 0) {
                 s_stop = !go;
                 if (go) {
                     EvRecord &rec = s_rec[e & 1];
                     rec.i = ei; rec.j = ej; rec.ty = ety; rec.slot = eslot; rec.psum = Psum;
-                    rec.pos = pos; rec.w = wrow;
-                    s_event_time = s_lg[e & 3] / Psum;  // residence time (kmc_events.cu:515)
+                    rec.pos = pos; rec.w = wrow; rec.fast = fast_rec;
                     s_nevents = e + 1;
                 }
                 n_chunks = 0;
                 n_rows = 0;
             }
         }
+        EV_TR(7);
         __syncthreads();  // ---- barrier A
+#ifdef KMC_EV_TRACE
+        tr_e = s_nevents - 1;
+#endif
+        EV_TR(1);
         EV_TICK(0);
         if (s_stop) break;
         const int ev_idx = s_nevents - 1;
         const int ei = s_rec[ev_idx & 1].i, ej = s_rec[ev_idx & 1].j;
-        // =============================== P (part 1): predict the next event's chunk from the UNREPAIRED sums ==========
-        int pchunk = -1;
-        double pnum = 0.0, pinc[8];
-        if (warp == PW && a.use_spec) {
-            const EvRecord rec = s_rec[ev_idx & 1];
-            if (rec.i >= 0) {
-                Scan256 sc;
-                double v[8];
+        i_select = false;
+        if (warp == PW) {
+            // =========================== P: the predictor -- runs beside Z / R1 / R2 with no barrier of its own ==========
+            // It reads the sums and rates while the other warps repair them.  Nothing it publishes is trusted as such: the
+            // selector accepts a prediction only if (a) the predicted chunk / super is not in this event's dirty list --
+            // then every array the prediction was derived from is untouched by this event, whatever the interleaving --
+            // and (b) the exact `number` of the next event falls in the published intervals.
+            if (a.use_spec) {
+                const EvRecord rec = s_rec[ev_idx & 1];
+                int pchunk = -1, pr = -1, pej = -1, ok = 0;
+                if (rec.i >= 0) {
+                    // the point the next draw will land on, in the coordinates of the sums BEFORE this event's repair: the
+                    // event removes (to first order) row i's total rate w, which sits at cumulative position pos
+                    double t = s_u1[(ev_idx + 1) & 3] * (rec.psum - rec.w);
+                    if (t >= rec.pos) t = t + rec.w;
+                    double prev, cur;
+                    double tinc[8];  // the selector of this event left its scan of the (still unrepaired) super sums
 #pragma unroll
-                for (int k = 0; k < 8; ++k) { v[k] = ss[32 * k + lane]; sc.a[k] = v[k]; }
-                warp_scan_256(sc);
-                // the point the next draw will land on, in the coordinates of the sums BEFORE this event's repair: the
-                // event removes (to first order) row i's total rate w, which sits at cumulative position pos
-                double t = s_u1[(ev_idx + 1) & 3] * (rec.psum - rec.w);
-                if (t >= rec.pos) t = t + rec.w;
-                double prev, cur;
-                const int ts = warp_pick_256(sc, v, t, &prev);
-                if (ts >= 0) {
-                    t = t - prev;
-                    double inc[8];
+                    for (int k = 0; k < 8; ++k) tinc[k] = s_top_incl[32 * k + lane];
+                    const int ts = warp_pick_incl(tinc, t, &prev, &cur, [&](double *vv) {
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) inc[k] = ci[KMC_CS(ts, k)];
-                    const int tc = warp_pick_incl(inc, t, &prev, &cur, [&](double *vv) {
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) vv[k] = cs[KMC_CS(ts, k)];
+                        for (int k = 0; k < 8; ++k) vv[k] = 0.0;  // no prefix exceeds t: no prediction
                     });
+                    int tc = -1;
+                    double inc[8];
+                    if (ts >= 0) {
+                        t = t - prev;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) inc[k] = ci[KMC_CS(ts, k)];
+                        tc = warp_pick_incl(inc, t, &prev, &cur, [&](double *vv) {
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) vv[k] = cs[KMC_CS(ts, k)];
+                        });
+                    }
                     if (tc >= 0) {
-                        pnum = t - prev;
+                        double pinc[8];
                         pchunk = ts * 256 + tc;
                         const double2 *src2 = reinterpret_cast<const double2 *>(a.rowincl + pchunk * 256 + 8 * lane);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {  // in flight across the barriers below
+                        for (int k = 0; k < 4; ++k) {
                             double2 t2 = src2[k];
                             pinc[2 * k] = t2.x; pinc[2 * k + 1] = t2.y;
                         }
+                        EV_TR(3);
+                        // (while the row prefixes are in flight)
+                        const double lo = warp_max_before(inc, tc);
+                        if (lane == 0) {
+                            s_pred.ts = ts; s_pred.tc = tc;
+                            s_pred.lo_c = lo; s_pred.hi_c = cur; s_pred.prev_c = prev;
+                        }
+                        const double pnum = t - prev;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) s_spec_incl[32 * k + lane] = pinc[k];
+                        const int rbase = pchunk * 256 + 8 * lane;
+                        const int tr = warp_pick_incl(pinc, pnum, &prev, &cur, [&](double *vv) {
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) vv[k] = (rbase + k < a.N) ? a.rowsum[rbase + k] : 0.0;
+                        });
+                        if (tr >= 0) {
+                            pr = pchunk * 256 + tr;
+                            const int base = pr * nn;
+                            double p0 = 0.0, p1 = 0.0;
+                            int nb0 = -1, nb1 = -1, ty0 = KMCB200_NULL_EVENT, ty1 = KMCB200_NULL_EVENT;
+                            if (lane < nn) { p0 = a.prob[base + lane]; nb0 = a.neigh[base + lane]; ty0 = a.type[base + lane]; }
+                            if (lane + 32 < nn) { p1 = a.prob[base + lane + 32]; nb1 = a.neigh[base + lane + 32]; ty1 = a.type[base + lane + 32]; }
+                            EV_TR(4);
+                            // (while the row is in flight)
+                            const double lo_r = warp_max_before(pinc, tr);
+                            const double pnum3 = pnum - prev;
+                            if (lane == 0) { s_pred.tr = tr; s_pred.lo_r = lo_r; s_pred.hi_r = cur; s_pred.prev_r = prev; }
+                            if (p0 > 0.0) { prefetch_l2(a.rev + nb0 * REV_STRIDE); prefetch_l2(a.rev + nb0 * REV_STRIDE + 32); }
+                            if (p1 > 0.0) { prefetch_l2(a.rev + nb1 * REV_STRIDE); prefetch_l2(a.rev + nb1 * REV_STRIDE + 32); }
+                            s_spec_p[lane] = p0; s_spec_p[lane + 32] = p1;
+                            s_spec_nb[lane] = nb0; s_spec_nb[lane + 32] = nb1;
+                            s_spec_ty[lane] = ty0; s_spec_ty[lane + 32] = ty1;
+                            // the slot the exact walk would take for pnum3, with the interval of `number` that leads to it
+                            const unsigned m0 = __ballot_sync(KMC_FULL_MASK, p0 > 0.0), m1 = __ballot_sync(KMC_FULL_MASK, p1 > 0.0);
+                            unsigned long long mm = ((unsigned long long)m1 << 32) | m0;
+                            int seln = -1;
+                            double acc = 0.0, accb = 0.0;
+                            while (mm) {
+                                const int n = __ffsll((long long)mm) - 1;
+                                mm &= mm - 1;
+                                const double pv = __shfl_sync(KMC_FULL_MASK, (n < 32) ? p0 : p1, n & 31);
+                                accb = acc;
+                                acc = acc + pv;
+                                if (acc > pnum3) { seln = n; break; }
+                            }
+                            if (seln >= 0) {
+                                pej = __shfl_sync(KMC_FULL_MASK, (seln < 32) ? nb0 : nb1, seln & 31);
+                                const int pty = __shfl_sync(KMC_FULL_MASK, (seln < 32) ? ty0 : ty1, seln & 31);
+                                if (lane == 0) {
+                                    s_pred.n = seln; s_pred.ej = pej; s_pred.ety = pty;
+                                    s_pred.acc_b = accb; s_pred.acc_a = acc;
+                                }
+                                ok = 1;
+                            }
+                        }
                     }
                 }
-            }
-            if (lane == 0) {
-                s_spec_chunk = pchunk;
-                s_spec_valid = (pchunk >= 0);  // cleared in R2 if a row of this chunk changes in the current event
-            }
-        }
-        // =============================== Z: zero-out ================================================================
-        // zero_out_events_split (kmc_events.cu:247-266): every slot whose row or neighbour is i or j.  Padded slots
-        // already hold rate 0 / NULL_EVENT, so rows i and j are cleared entirely; slots of other rows pointing at i / j
-        // come from the reverse index.  4 warps (one per scheduler): the phase is two dependent round trips, not work.
-        if (ei >= 0 && tid < 2 * REV_STRIDE) {
-            const int s_site = (tid < REV_STRIDE) ? ei : ej;
-            const int q = tid & (REV_STRIDE - 1);
-            const int packed = a.rev[s_site * REV_STRIDE + q];
-            if (q < nn) {  // the event's own rows
-                const int sl = s_site * nn + q;
-                a.prob[sl] = 0.0;
-                a.type[sl] = KMCB200_NULL_EVENT;
-            }
-            if (q == 0) {  // ... whose sums become +0.0
-                a.rowsum[s_site] = 0.0;
-                const int c = s_site >> 8;
-                const unsigned bit = 1u << (c & 31);
-                if (!(atomicOr(&chunk_bits[c >> 5], bit) & bit)) {
-                    chunk_list[atomicAdd(&n_chunks, 1)] = c;
-                    if (atomicAdd(&super_cnt[c >> 8], 1) == 0) atomicAdd(&n_supers, 1);
-                }
-            }
-            if (packed >= 0) {
-                const int rr = packed >> 6;
-                const int sl = rr * nn + (packed & 63);
-                // a slot that already holds rate 0 does not change its row: only rows that lose a non-zero rate need
-                // their sums repaired (their recomputed sums would be bit-identical anyway)
-                const double oldp = a.prob[sl];
-                a.type[sl] = KMCB200_NULL_EVENT;
-                if (oldp != 0.0) {
-                    a.prob[sl] = 0.0;
-                    if (rr != ei && rr != ej) rows_list[atomicAdd(&n_rows, 1)] = rr;
-                }
-            }
-        }
-        __syncthreads();  // ---- barrier B1
-        EV_TICK(1);
-        // =============================== R1: row sums, one warp per row that lost a rate ===========================
-        // (a row listed twice -- it lost a rate to i and one to j -- is recomputed twice with the same result)
-        if (warp < NCW) {
-            const int nd = n_rows;
-            for (int qq = warp; qq < nd; qq += NCW) {
-                const int rr = rows_list[qq];
-                const int pb = rr * nn;
-                const double p0 = (lane < nn) ? a.prob[pb + lane] : 0.0;
-                const double p1 = (lane + 32 < nn) ? a.prob[pb + lane + 32] : 0.0;
-                const double sacc = warp_row_sum(p0, p1);
-                if (lane == 0) {
-                    a.rowsum[rr] = sacc;
-                    const int c = rr >> 8;
-                    const unsigned bit = 1u << (c & 31);
-                    if (!(atomicOr(&chunk_bits[c >> 5], bit) & bit)) {
-                        chunk_list[atomicAdd(&n_chunks, 1)] = c;
-                        if (atomicAdd(&super_cnt[c >> 8], 1) == 0) atomicAdd(&n_supers, 1);
+                // ---- stage the predicted event's zero-out inputs: the reverse-index rows of its two sites (issued before
+                // the prediction is published, consumed after)
+                int pk[4];
+                if (ok) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int q = lane + 32 * u;
+                        pk[u] = a.rev[((q < REV_STRIDE) ? pr : pej) * REV_STRIDE + (q & (REV_STRIDE - 1))];
                     }
                 }
-            }
-        }
-        __syncthreads();  // ---- barrier B2
-        EV_TICK(3);
-        // =============================== R2 / H / P: repair, housekeeping, speculation; election of the next selector =
-        i_select = false;
-        const int nc = n_chunks;
-        if (warp == PW) {
-            if (a.use_spec) {
-                // ---- P (part 2): the predicted row inside the predicted chunk, its slots -> shared memory ----------
-                int pr = -1;
+                EV_TR(5);
+                // what was read above is untouched by this event iff the predicted chunk (row prefixes, rates) / super (chunk
+                // prefixes) is not in this event's dirty list, which is complete once barrier B2 has been passed
+                int clean = 0;
                 if (pchunk >= 0) {
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) s_spec_incl[32 * k + lane] = pinc[k];
-                    double prev, cur;
-                    const int rbase = pchunk * 256 + 8 * lane;
-                    const int tr = warp_pick_incl(pinc, pnum, &prev, &cur, [&](double *vv) {
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) vv[k] = (rbase + k < a.N) ? a.rowsum[rbase + k] : 0.0;
-                    });
-                    if (tr >= 0) {
-                        pr = pchunk * 256 + tr;
-                        const int base = pr * nn;
-                        double p0 = 0.0, p1 = 0.0;
-                        int nb0 = -1, nb1 = -1, ty0 = KMCB200_NULL_EVENT, ty1 = KMCB200_NULL_EVENT;
-                        if (lane < 2) prefetch_l2(a.rev + pr * REV_STRIDE + 32 * lane);
-                        if (lane < nn) { p0 = a.prob[base + lane]; nb0 = a.neigh[base + lane]; ty0 = a.type[base + lane]; }
-                        if (lane + 32 < nn) { p1 = a.prob[base + lane + 32]; nb1 = a.neigh[base + lane + 32]; ty1 = a.type[base + lane + 32]; }
-                        if (p0 > 0.0) { prefetch_l2(a.rev + nb0 * REV_STRIDE); prefetch_l2(a.rev + nb0 * REV_STRIDE + 32); }
-                        if (p1 > 0.0) { prefetch_l2(a.rev + nb1 * REV_STRIDE); prefetch_l2(a.rev + nb1 * REV_STRIDE + 32); }
-                        s_spec_p[lane] = p0; s_spec_p[lane + 32] = p1;
-                        s_spec_nb[lane] = nb0; s_spec_nb[lane + 32] = nb1;
-                        s_spec_ty[lane] = ty0; s_spec_ty[lane + 32] = ty1;
+                    while (*(volatile int *)&s_b2_event < ev_idx + 1) { }
+                    __threadfence_block();
+                    const int ndc = *(volatile int *)&n_chunks;
+                    bool dc = false, dsup = false;
+                    for (int q = lane; q < ndc; q += 32) {
+                        const int c = chunk_list[q];
+                        dc |= (c == pchunk);
+                        dsup |= ((c >> 8) == (pchunk >> 8));
                     }
+                    clean = (__any_sync(KMC_FULL_MASK, dc) ? 0 : 1) | (__any_sync(KMC_FULL_MASK, dsup) ? 0 : 2);
                 }
                 __syncwarp();
                 if (lane == 0) {
+                    s_spec_chunk = pchunk;
                     s_spec_r = pr;
+                    s_pred_ok = ok;
+                    s_pred_clean = clean;
                     __threadfence_block();
                     *(volatile int *)&s_spec_ready = ev_idx + 1;
                 }
+                EV_TR(2);
+                if (ok) {
+                    // ... and the rates of the slots they name.  Such a slot is written by THIS event's zero-out only if its
+                    // row is one of this event's two sites (then it ends up 0) or if it makes the predicted row dirty (then
+                    // the prediction is rejected), so the values are those the next zero-out would read -- before or after
+                    // this event's zero-out ran.
+                    const int nb = (ev_idx + 1) & 1;
+                    double po[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int rr = pk[u] >> 6;
+                        po[u] = (pk[u] >= 0 && rr != rec.i && rr != rec.j) ? a.prob[rr * nn + (pk[u] & 63)] : 0.0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        s_pz_packed[nb][lane + 32 * u] = pk[u];
+                        s_pz_oldp[nb][lane + 32 * u] = po[u];
+                        if (pk[u] >= 0 && po[u] != 0.0) {  // rows the next R1 will sum: towards L2 now
+                            const double *rowp = a.prob + (pk[u] >> 6) * nn;
+                            prefetch_l2(rowp); prefetch_l2(rowp + 16); prefetch_l2(rowp + 32); prefetch_l2(rowp + nn - 1);
+                        }
+                    }
+                    if (lane == 0) s_pz_event[nb] = ev_idx + 1;
+                }
             }
         } else if (warp == HW) {
-            // ---- H: event application, log, uniforms of event ev_idx + 2 -----------------------------------------
+            // =========================== H: housekeeping -- beside Z / R1 / R2, no barrier of its own ======================
+            // residence time of this event (kmc_events.cu:515; the next selector's stop test waits for it), event
+            // application, log, uniforms of event ev_idx + 2
             if (lane == 0) {
                 const EvRecord rec = s_rec[ev_idx & 1];
+                s_event_time = s_lg[ev_idx & 3] / rec.psum;
+                __threadfence_block();
+                *(volatile int *)&s_h_done = ev_idx + 1;
                 if (rec.i >= 0) {  // execute_event: kmc_events.cu:305-328
                     const int i = rec.i, j = rec.j, ty = rec.ty;
                     if (ty == KMCB200_VACANCY_GENERATION) {
@@ -798,50 +945,169 @@ __global__ void __launch_bounds__(EV_THREADS, 1) event_loop_kernel(EvLoopArgs a)
                 s_lg[e2 & 3] = -log(evrng_next_double(rng));
             }
         } else {
-            if (nc == 0) i_select = (warp == 0);  // nothing changed (no selectable event): warp 0 selects again
-            for (int qq = warp; qq < nc; qq += NCW) {
-                const int c = chunk_list[qq];
-                Scan256 sc;
-                const double2 *src2 = reinterpret_cast<const double2 *>(a.rowsum + c * 256 + 8 * lane);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) { double2 t2 = src2[k]; sc.a[2 * k] = t2.x; sc.a[2 * k + 1] = t2.y; }
-                warp_scan_256(sc);
-                double2 *dst2 = reinterpret_cast<double2 *>(a.rowincl + c * 256 + 8 * lane);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) dst2[k] = make_double2(scan_incl(sc, 2 * k), scan_incl(sc, 2 * k + 1));
-                const int sidx = c >> 8;
-                int left = 0;
-                if (lane == 0) {
-                    cs[KMC_CIDX(c)] = sc.total;
-                    chunk_bits[c >> 5] = 0u;  // every set bit of this word belongs to a dirty chunk handled in this phase
-                    if (c == s_spec_chunk) s_spec_valid = 0;  // the predictor's copies of this chunk are stale
-                    __threadfence_block();
-                    left = atomicSub(&super_cnt[sidx], 1) - 1;
+            // =============================== Z: zero-out ================================================================
+            // zero_out_events_split (kmc_events.cu:247-266): every slot whose row or neighbour is i or j.  Padded slots
+            // already hold rate 0 / NULL_EVENT, so rows i and j are cleared entirely; slots of other rows pointing at i / j
+            // come from the reverse index.  4 warps (one per scheduler): the phase is two dependent round trips, not work.
+            if (ei >= 0 && tid < 2 * REV_STRIDE) {
+                const int s_site = (tid < REV_STRIDE) ? ei : ej;
+                const int q = tid & (REV_STRIDE - 1);
+                // the predictor staged this event's inputs during the previous event (it finished before barrier A)
+                const bool staged = s_rec[ev_idx & 1].fast && s_pz_event[ev_idx & 1] == ev_idx;
+                const int packed = staged ? s_pz_packed[ev_idx & 1][tid] : a.rev[s_site * REV_STRIDE + q];
+                if (q < nn) {  // the event's own rows
+                    const int sl = s_site * nn + q;
+                    a.prob[sl] = 0.0;
+                    a.type[sl] = KMCB200_NULL_EVENT;
                 }
-                left = __shfl_sync(KMC_FULL_MASK, left, 0);
-                if (left == 0) {
-                    // ---- this warp finished the last dirty chunk of super sidx: re-scan the super -------------
-                    __threadfence_block();
-                    Scan256 su;
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) su.a[k] = cs[KMC_CS(sidx, k)];
-                    warp_scan_256(su);
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) ci[KMC_CS(sidx, k)] = scan_incl(su, k);
-                    int sleft = 0;
-                    if (lane == 0) {
-                        ss[tpos(sidx)] = su.total;
-                        __threadfence_block();
-                        sleft = atomicSub(&n_supers, 1) - 1;
+                if (q == 0) {  // ... whose sums become +0.0
+                    a.rowsum[s_site] = 0.0;
+                    const int c = s_site >> 8;
+                    const unsigned bit = 1u << (c & 31);
+                    if (!(atomicOr(&chunk_bits[c >> 5], bit) & bit)) {
+                        chunk_list[atomicAdd(&n_chunks, 1)] = c;
+                        if (atomicAdd(&super_cnt[c >> 8], 1) == 0) atomicAdd(&n_supers, 1);
                     }
-                    sleft = __shfl_sync(KMC_FULL_MASK, sleft, 0);
-                    if (sleft == 0) {  // ... and the last dirty super: this warp selects the next event
-                        __threadfence_block();
+                }
+                if (packed >= 0) {
+                    const int rr = packed >> 6;
+                    const int sl = rr * nn + (packed & 63);
+                    // a slot that already holds rate 0 does not change its row: only rows that lose a non-zero rate need
+                    // their sums repaired (their recomputed sums would be bit-identical anyway)
+                    const double oldp = staged ? s_pz_oldp[ev_idx & 1][tid] : a.prob[sl];
+                    a.type[sl] = KMCB200_NULL_EVENT;
+                    if (oldp != 0.0) {
+                        a.prob[sl] = 0.0;
+                        if (rr != ei && rr != ej) rows_list[atomicAdd(&n_rows, 1)] = rr;
+                    }
+                }
+            }
+            EV_TR(2);
+            asm volatile("bar.sync 1, %0;" ::"n"(NCW * 32) : "memory");  // ---- barrier B1 (the NCW working warps)
+            EV_TR(3);
+            EV_TICK(1);
+            // =============================== R1: row sums, one warp per row that lost a rate ===========================
+            // (a row listed twice -- it lost a rate to i and one to j -- is recomputed twice with the same result)
+            if (warp < NCW) {
+                const int nd = n_rows;
+                for (int qq = warp; qq < nd; qq += NCW) {
+                    const int rr = rows_list[qq];
+                    const int pb = rr * nn;
+                    const double p0 = (lane < nn) ? a.prob[pb + lane] : 0.0;
+                    const double p1 = (lane + 32 < nn) ? a.prob[pb + lane + 32] : 0.0;
+                    if (lane == 0) {  // dirty-chunk bookkeeping while the row is in flight
+                        const int c = rr >> 8;
+                        const unsigned bit = 1u << (c & 31);
+                        if (!(atomicOr(&chunk_bits[c >> 5], bit) & bit)) {
+                            chunk_list[atomicAdd(&n_chunks, 1)] = c;
+                            if (atomicAdd(&super_cnt[c >> 8], 1) == 0) atomicAdd(&n_supers, 1);
+                        }
+                    }
+                    const double sacc = warp_row_sum(p0, p1);
+                    if (lane == 0) a.rowsum[rr] = sacc;
+                }
+            }
+            EV_TR(4);
+            asm volatile("bar.sync 1, %0;" ::"n"(NCW * 32) : "memory");  // ---- barrier B2
+            EV_TR(5);
+            EV_TICK(3);
+            const int nc = n_chunks;
+            if (tid == 0) *(volatile int *)&s_b2_event = ev_idx + 1;  // (the barrier ordered the dirty lists before this)
+            {
+                if (nc == 0) i_select = (warp == 0);  // nothing changed (no selectable event): warp 0 selects again
+                // ---- the common case, one or two dirty chunks in one super: ONE warp repairs them (the two chunk scans
+                // interleaved), re-scans the super and goes on to select -- no hand-over, no atomics, no fences
+                const int c0 = chunk_list[0], c1 = chunk_list[nc > 0 ? nc - 1 : 0];
+                const bool solo = (nc == 1 || nc == 2) && ((c0 >> 8) == (c1 >> 8));
+                if (solo) {
+                    if (warp == 0) {
+                        Scan256 sa, sb;
+                        const double2 *srca = reinterpret_cast<const double2 *>(a.rowsum + c0 * 256 + 8 * lane);
+                        const double2 *srcb = reinterpret_cast<const double2 *>(a.rowsum + c1 * 256 + 8 * lane);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) { double2 t2 = srca[k]; sa.a[2 * k] = t2.x; sa.a[2 * k + 1] = t2.y; }
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) { double2 t2 = srcb[k]; sb.a[2 * k] = t2.x; sb.a[2 * k + 1] = t2.y; }
+                        warp_scan_256x2(sa, sb);
+                        EV_TR(12);
+                        double2 *dsta = reinterpret_cast<double2 *>(a.rowincl + c0 * 256 + 8 * lane);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) dsta[k] = make_double2(scan_incl(sa, 2 * k), scan_incl(sa, 2 * k + 1));
+                        if (nc == 2) {
+                            double2 *dstb = reinterpret_cast<double2 *>(a.rowincl + c1 * 256 + 8 * lane);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) dstb[k] = make_double2(scan_incl(sb, 2 * k), scan_incl(sb, 2 * k + 1));
+                        }
+                        const int sidx = c0 >> 8;
+                        if (lane == 0) {
+                            cs[KMC_CIDX(c0)] = sa.total;
+                            cs[KMC_CIDX(c1)] = sb.total;  // (c1 == c0 and sb == sa for a single chunk)
+                            chunk_bits[c0 >> 5] = 0u;
+                            chunk_bits[c1 >> 5] = 0u;
+                            super_cnt[sidx] = 0;
+                            n_supers = 0;
+                        }
+                        __syncwarp();
+                        EV_TR(13);
+                        Scan256 su;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) su.a[k] = cs[KMC_CS(sidx, k)];
+                        warp_scan_256(su);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) ci[KMC_CS(sidx, k)] = scan_incl(su, k);
+                        if (lane == 0) ss[tpos(sidx)] = su.total;
+                        __syncwarp();
+                        EV_TR(14);
                         i_select = true;
+                    }
+                } else
+                for (int qq = warp; qq < nc; qq += NCW) {
+                    const int c = chunk_list[qq];
+                    Scan256 sc;
+                    const double2 *src2 = reinterpret_cast<const double2 *>(a.rowsum + c * 256 + 8 * lane);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { double2 t2 = src2[k]; sc.a[2 * k] = t2.x; sc.a[2 * k + 1] = t2.y; }
+                    warp_scan_256(sc);
+                    if (qq == warp) EV_TR(12);
+                    double2 *dst2 = reinterpret_cast<double2 *>(a.rowincl + c * 256 + 8 * lane);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) dst2[k] = make_double2(scan_incl(sc, 2 * k), scan_incl(sc, 2 * k + 1));
+                    const int sidx = c >> 8;
+                    int left = 0;
+                    if (lane == 0) {
+                        cs[KMC_CIDX(c)] = sc.total;
+                        chunk_bits[c >> 5] = 0u;  // every set bit of this word belongs to a dirty chunk handled in this phase
+                        __threadfence_block();
+                        left = atomicSub(&super_cnt[sidx], 1) - 1;
+                    }
+                    left = __shfl_sync(KMC_FULL_MASK, left, 0);
+                    if (qq == warp) EV_TR(13);
+                    if (left == 0) {
+                        // ---- this warp finished the last dirty chunk of super sidx: re-scan the super -------------
+                        __threadfence_block();
+                        Scan256 su;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) su.a[k] = cs[KMC_CS(sidx, k)];
+                        warp_scan_256(su);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) ci[KMC_CS(sidx, k)] = scan_incl(su, k);
+                        int sleft = 0;
+                        if (lane == 0) {
+                            ss[tpos(sidx)] = su.total;
+                            __threadfence_block();
+                            sleft = atomicSub(&n_supers, 1) - 1;
+                        }
+                        sleft = __shfl_sync(KMC_FULL_MASK, sleft, 0);
+                        EV_TR(14);
+                        if (sleft == 0) {  // ... and the last dirty super: this warp selects the next event
+                            __threadfence_block();
+                            i_select = true;
+                        }
                     }
                 }
             }
         }
+        EV_TR(6);
         EV_TICK(2);
     }
 #undef KMC_CIDX
@@ -861,6 +1127,9 @@ __global__ void __launch_bounds__(EV_THREADS, 1) event_loop_kernel(EvLoopArgs a)
         a.result->error = 0;
 #ifdef KMC_EV_PROFILE
         if (a.phase_cycles) for (int q = 0; q < 16; ++q) a.phase_cycles[q] = (q >= 4) ? (long long)s_prof[q] : ph[q];
+#endif
+#ifdef KMC_EV_TRACE
+        if (a.phase_cycles) for (int q = 0; q < 8; ++q) a.phase_cycles[64 * 16 * 16 + q] = s_tr_cnt[q];
 #endif
     }
 }
@@ -1070,6 +1339,10 @@ extern "C" int kmcb200_execute_kmc_step(kmcb200_ctx *ctx, kmcb200_events *ev, in
 #ifdef KMC_EV_PROFILE
     KMC_TRY(kmc_scratch(ctx, 5, 16 * sizeof(long long), (void **)&a.phase_cycles));
 #endif
+#ifdef KMC_EV_TRACE
+    KMC_TRY(kmc_scratch(ctx, 5, (64 * 16 * 16 + 8) * sizeof(long long), (void **)&a.phase_cycles));
+    KMC_CUDA(cudaMemsetAsync(a.phase_cycles, 0, (64 * 16 * 16 + 8) * sizeof(long long), ctx->stream));
+#endif
     // chunk sums + their stored prefixes live in shared memory when they fit (up to ~3.2 M sites); larger devices
     // read them from L2
     size_t dyn = (size_t)(2 * ev->nsuper * 256) * sizeof(double);
@@ -1116,6 +1389,25 @@ extern "C" int kmcb200_execute_kmc_step(kmcb200_ctx *ctx, kmcb200_events *ev, in
         fprintf(stderr, "[ev profile] events=%d cycles/event:", h->n_events);
         for (int q = 0; q < 16; ++q) fprintf(stderr, " p%d=%.0f", q, (double)ph[q] / (h->n_events > 0 ? h->n_events : 1));
         fprintf(stderr, "\n");
+    }
+#endif
+#ifdef KMC_EV_TRACE
+    if (getenv("KMCB200_EV_TRACE_FILE") && h->n_events > EV_TRACE_FIRST + 64) {
+        static int dumped = 0;
+        if (dumped++ == 1) {   // second superstep
+            std::vector<long long> t(64 * 16 * 16 + 8);
+            cudaMemcpy(t.data(), a.phase_cycles, t.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+            fprintf(stderr, "[ev trace] events %lld: fast-path %lld, pred_ok %lld, super_ok %lld, chunk_valid %lld, super match %lld\n",
+                    (long long)h->n_events, t[64 * 16 * 16], t[64 * 16 * 16 + 1], t[64 * 16 * 16 + 2], t[64 * 16 * 16 + 3], t[64 * 16 * 16 + 4]);
+            FILE *f = fopen(getenv("KMCB200_EV_TRACE_FILE"), "w");
+            for (int e = 0; e < 64; ++e)
+                for (int w = 0; w < 16; ++w) {
+                    fprintf(f, "%d %d", e, w);
+                    for (int k = 0; k < 16; ++k) fprintf(f, " %lld", t[(e * 16 + w) * 16 + k]);
+                    fprintf(f, "\n");
+                }
+            fclose(f);
+        }
     }
 #endif
     ev->last_n_events = h->n_events;
