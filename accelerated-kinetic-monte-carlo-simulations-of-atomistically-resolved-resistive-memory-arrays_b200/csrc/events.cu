@@ -46,6 +46,13 @@ struct kmcb200_events {
     size_t l2_window_bytes = 0;  // 0: no persisting-L2 window (not supported / disabled)
     float l2_hit_ratio = 1.0f;
     int *rev = nullptr;  // N * REV_STRIDE
+    // revpos[r*nn + n] = position of slot (r, n) inside the reverse-index row of its neighbour (static);
+    // nzflag[s*64 + q] == gen  <=>  the slot named by rev[s*64 + q] may hold a non-zero rate in the current event list
+    // (set by the rate build, cleared when the slot is zeroed through that reverse-index entry; the slots of an event's own
+    // two rows keep their flags -- a stale "may" only costs a redundant, bit-identical row sum).  gen is
+    // 1..255 and advances with every build, so the flags of older lists expire without a pass over the array.
+    unsigned char *revpos = nullptr, *nzflag = nullptr;
+    int gen = 0;
     unsigned *mt = nullptr;  // 624 words + pos
     int *log = nullptr;
     double *log_psum = nullptr;
@@ -62,14 +69,18 @@ constexpr int REV_STRIDE = 64;  // max number of rows that list a given site (in
 // reverse neighbour index, fixed stride: rev[s*64 + q] = (r << 6) | n for the slots (r, n) with neigh[r][n] == s,
 // -1 padded (r < 2^24, n < 64: no division in the event loop)
 __global__ void rev_fill_kernel(const int *__restrict__ neigh, long long total, int nn, int *__restrict__ fill,
-                                int *__restrict__ rev, int *__restrict__ overflow) {
+                                int *__restrict__ rev, unsigned char *__restrict__ revpos, int *__restrict__ overflow) {
     long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= total) return;
     int j = neigh[s];
     if (j >= 0) {
         int pos = atomicAdd(fill + j, 1);
-        if (pos < REV_STRIDE - 1) rev[(size_t)j * REV_STRIDE + pos] = (int)((s / nn) << 6) | (int)(s % nn);  // last entry stays free (-1)
-        else atomicExch(overflow, 1);
+        if (pos < REV_STRIDE - 1) {  // last entry stays free (-1)
+            rev[(size_t)j * REV_STRIDE + pos] = (int)((s / nn) << 6) | (int)(s % nn);
+            revpos[s] = (unsigned char)pos;
+        } else {
+            atomicExch(overflow, 1);
+        }
     }
 }
 
@@ -277,7 +288,9 @@ __global__ void __launch_bounds__(256) build_rates_kernel(int N, int nn, const i
                                                          const int *__restrict__ charge, EvEnergies E,
                                                          double *__restrict__ prob, unsigned char *__restrict__ type,
                                                          double *__restrict__ rowsum, double *__restrict__ chunksum,
-                                                         double *__restrict__ rowincl) {
+                                                         double *__restrict__ rowincl,
+                                                         const unsigned char *__restrict__ revpos,
+                                                         unsigned char *__restrict__ nzflag, int gen) {
     __shared__ double rs[256];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int row0 = blockIdx.x * 256 + w * 32;
@@ -299,12 +312,14 @@ __global__ void __launch_bounds__(256) build_rates_kernel(int N, int nn, const i
                     if (j >= 0 && j < N)
                         P0 = event_rate(i, j, el_i, c_i, pot_i, xi, yi, zi, element, charge, pot, layer, x, y, z, E, kT,
                                         freq, sigma, k, e0);
+                    if (P0 != 0.0) nzflag[(size_t)j * REV_STRIDE + revpos[base + lane]] = (unsigned char)gen;
                 }
                 if (lane + 32 < nn) {
                     int j = neigh[base + lane + 32];
                     if (j >= 0 && j < N)
                         P1 = event_rate(i, j, el_i, c_i, pot_i, xi, yi, zi, element, charge, pot, layer, x, y, z, E, kT,
                                         freq, sigma, k, e1);
+                    if (P1 != 0.0) nzflag[(size_t)j * REV_STRIDE + revpos[base + lane + 32]] = (unsigned char)gen;
                 }
             }
             if (lane < nn) { prob[base + lane] = P0; type[base + lane] = (unsigned char)e0; }
@@ -394,6 +409,9 @@ struct EvLoopArgs {
     unsigned char *type;
     double *rowsum, *chunksum, *supersum, *rowincl, *chunkincl;
     const int *rev;
+    const unsigned char *revpos;  // position of each slot in its neighbour's reverse-index row
+    unsigned char *nzflag;        // == gen: the slot named by the reverse-index entry may hold a non-zero rate
+    int gen;
     int *element, *charge;
     unsigned *mt_state;  // 624 + pos
     double inv_freq_threshold;  // 1/freq
@@ -406,6 +424,11 @@ struct EvLoopArgs {
     long long *phase_cycles;  // 16 counters (KMC_EV_PROFILE builds)
 };
 
+// Hand-overs between warps of the one CTA through SHARED memory (data stores, then a volatile flag store; volatile flag
+// load, then data loads): a warp's shared-memory accesses are performed in program order, so only the compiler has to be
+// kept from reordering them.  (A membar.cta would also wait for the warp's outstanding GLOBAL accesses -- a full round
+// trip on the critical path.)  Hand-overs of global data go through the block barriers.
+#define KMC_CBAR() asm volatile("" ::: "memory")
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // Shared-memory layout of a 256-group that one warp scans (lane l owns elements 8l..8l+7): element t lives at
@@ -503,7 +526,10 @@ __global__ void __launch_bounds__(EV_THREADS, 1) event_loop_kernel(EvLoopArgs a)
     // zero-out of event e may still read buffer e&1)
     __shared__ int s_pz_packed[2][2 * REV_STRIDE];   // reverse-index rows of the predicted event's two sites ...
     __shared__ double s_pz_oldp[2][2 * REV_STRIDE];  // ... and the rates those slots hold
+    __shared__ int s_pz_rows[2][2 * REV_STRIDE];     // ... compacted: the rows (other than the two sites) that lose a rate
+    __shared__ int s_pz_nrows[2];
     __shared__ int s_pz_event[2];                    // index of the event each buffer was staged for
+    __shared__ int s_pz_pr, s_pz_pej, s_pz_req1, s_pz_req;      // predictor -> housekeeping warp: the predicted pair, = e + 1 when set
     __shared__ int s_pred_ok;                        // the prediction reached the slot level
     __shared__ int s_h_done;                    // = e + 1 once the residence time of event e is stored
     __shared__ int s_b2_event;                  // = e + 1 once event e passed barrier B2 (its dirty lists are complete)
@@ -556,7 +582,7 @@ __global__ void __launch_bounds__(EV_THREADS, 1) event_loop_kernel(EvLoopArgs a)
         n_rows = 0;
         n_chunks = 0;
         n_supers = 0;
-        s_spec_chunk = -1; s_spec_r = -1; s_spec_ready = 0; s_h_done = 0; s_b2_event = 0; s_pred_clean = 0; s_pred_ok = 0; s_pz_event[0] = s_pz_event[1] = -1;
+        s_spec_chunk = -1; s_spec_r = -1; s_spec_ready = 0; s_h_done = 0; s_b2_event = 0; s_pred_clean = 0; s_pz_req = 0; s_pz_req1 = 0; s_pz_pr = -1; s_pz_pej = -1; s_pred_ok = 0; s_pz_event[0] = s_pz_event[1] = -1;
     }
     __syncthreads();
     if (tid == 0) {
@@ -579,7 +605,7 @@ __global__ void __launch_bounds__(EV_THREADS, 1) event_loop_kernel(EvLoopArgs a)
         if (i_select) {
             const int e = s_nevents;  // index of the event selected now
             while (*(volatile int *)&s_h_done < e) { }  // residence time of event e - 1
-            __threadfence_block();
+            KMC_CBAR();
             const bool go = (s_event_time < a.inv_freq_threshold) && (a.max_events <= 0 || e < a.max_events);
             int ei = -1, ej = -1, ety = KMCB200_NULL_EVENT, eslot = -1;
             double Psum = 0.0, pos = 0.0, wrow = 0.0;
@@ -612,7 +638,7 @@ __global__ void __launch_bounds__(EV_THREADS, 1) event_loop_kernel(EvLoopArgs a)
                 int pc = -1;
                 if (ts >= 0 && a.use_spec) {
                     while (*(volatile int *)&s_spec_ready < e) { }
-                    __threadfence_block();
+                    KMC_CBAR();
                     EV_TR(9);
                     pc = *(volatile int *)&s_spec_chunk;
                     const int clean = *(volatile int *)&s_pred_clean;  // the predictor's verdict on the dirty lists
@@ -817,6 +843,11 @@ __global__ void __launch_bounds__(EV_THREADS, 1) event_loop_kernel(EvLoopArgs a)
                             int nb0 = -1, nb1 = -1, ty0 = KMCB200_NULL_EVENT, ty1 = KMCB200_NULL_EVENT;
                             if (lane < nn) { p0 = a.prob[base + lane]; nb0 = a.neigh[base + lane]; ty0 = a.type[base + lane]; }
                             if (lane + 32 < nn) { p1 = a.prob[base + lane + 32]; nb1 = a.neigh[base + lane + 32]; ty1 = a.type[base + lane + 32]; }
+                            if (lane == 0) {  // the housekeeping warp starts staging this site's half now
+                                s_pz_pr = pr;
+                                KMC_CBAR();
+                                *(volatile int *)&s_pz_req1 = ev_idx + 1;
+                            }
                             EV_TR(4);
                             // (while the row is in flight)
                             const double lo_r = warp_max_before(pinc, tr);
@@ -852,15 +883,13 @@ __global__ void __launch_bounds__(EV_THREADS, 1) event_loop_kernel(EvLoopArgs a)
                         }
                     }
                 }
-                // ---- stage the predicted event's zero-out inputs: the reverse-index rows of its two sites (issued before
-                // the prediction is published, consumed after)
-                int pk[4];
-                if (ok) {
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int q = lane + 32 * u;
-                        pk[u] = a.rev[((q < REV_STRIDE) ? pr : pej) * REV_STRIDE + (q & (REV_STRIDE - 1))];
-                    }
+                // ---- hand the predicted pair to the housekeeping warp, which stages that event's zero-out inputs
+                if (lane == 0) {
+                    s_pz_pr = pr;
+                    s_pz_pej = ok ? pej : -1;
+                    KMC_CBAR();
+                    *(volatile int *)&s_pz_req1 = ev_idx + 1;
+                    *(volatile int *)&s_pz_req = ev_idx + 1;
                 }
                 EV_TR(5);
                 // what was read above is untouched by this event iff the predicted chunk (row prefixes, rates) / super (chunk
@@ -868,7 +897,7 @@ __global__ void __launch_bounds__(EV_THREADS, 1) event_loop_kernel(EvLoopArgs a)
                 int clean = 0;
                 if (pchunk >= 0) {
                     while (*(volatile int *)&s_b2_event < ev_idx + 1) { }
-                    __threadfence_block();
+                    KMC_CBAR();
                     const int ndc = *(volatile int *)&n_chunks;
                     bool dc = false, dsup = false;
                     for (int q = lane; q < ndc; q += 32) {
@@ -884,33 +913,10 @@ __global__ void __launch_bounds__(EV_THREADS, 1) event_loop_kernel(EvLoopArgs a)
                     s_spec_r = pr;
                     s_pred_ok = ok;
                     s_pred_clean = clean;
-                    __threadfence_block();
+                    KMC_CBAR();
                     *(volatile int *)&s_spec_ready = ev_idx + 1;
                 }
                 EV_TR(2);
-                if (ok) {
-                    // ... and the rates of the slots they name.  Such a slot is written by THIS event's zero-out only if its
-                    // row is one of this event's two sites (then it ends up 0) or if it makes the predicted row dirty (then
-                    // the prediction is rejected), so the values are those the next zero-out would read -- before or after
-                    // this event's zero-out ran.
-                    const int nb = (ev_idx + 1) & 1;
-                    double po[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int rr = pk[u] >> 6;
-                        po[u] = (pk[u] >= 0 && rr != rec.i && rr != rec.j) ? a.prob[rr * nn + (pk[u] & 63)] : 0.0;
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        s_pz_packed[nb][lane + 32 * u] = pk[u];
-                        s_pz_oldp[nb][lane + 32 * u] = po[u];
-                        if (pk[u] >= 0 && po[u] != 0.0) {  // rows the next R1 will sum: towards L2 now
-                            const double *rowp = a.prob + (pk[u] >> 6) * nn;
-                            prefetch_l2(rowp); prefetch_l2(rowp + 16); prefetch_l2(rowp + 32); prefetch_l2(rowp + nn - 1);
-                        }
-                    }
-                    if (lane == 0) s_pz_event[nb] = ev_idx + 1;
-                }
             }
         } else if (warp == HW) {
             // =========================== H: housekeeping -- beside Z / R1 / R2, no barrier of its own ======================
@@ -919,7 +925,7 @@ __global__ void __launch_bounds__(EV_THREADS, 1) event_loop_kernel(EvLoopArgs a)
             if (lane == 0) {
                 const EvRecord rec = s_rec[ev_idx & 1];
                 s_event_time = s_lg[ev_idx & 3] / rec.psum;
-                __threadfence_block();
+                KMC_CBAR();
                 *(volatile int *)&s_h_done = ev_idx + 1;
                 if (rec.i >= 0) {  // execute_event: kmc_events.cu:305-328
                     const int i = rec.i, j = rec.j, ty = rec.ty;
@@ -944,57 +950,106 @@ __global__ void __launch_bounds__(EV_THREADS, 1) event_loop_kernel(EvLoopArgs a)
                 s_u1[e2 & 3] = evrng_next_double(rng);
                 s_lg[e2 & 3] = -log(evrng_next_double(rng));
             }
+            __syncwarp();
+            if (a.use_spec) {
+                // ---- stage the zero-out inputs of the PREDICTED next event: the reverse-index rows of its two sites, the
+                // "may be non-zero" flags of the slots they name (one round trip together with the rows -- reading the
+                // rates themselves would be a second, dependent one), and the compacted list of the rows that lose a rate.
+                // A flag can only err towards "non-zero" (a redundant, bit-identical row sum), never towards "zero".
+                const int ri = s_rec[ev_idx & 1].i, rj = s_rec[ev_idx & 1].j;
+                const int nb = (ev_idx + 1) & 1;
+                int pk[4] = {-1, -1, -1, -1};
+                int fl[4] = {0, 0, 0, 0};
+                // first half: the predicted row's site, known one round trip before its partner
+                while (*(volatile int *)&s_pz_req1 < ev_idx + 1) { }
+                KMC_CBAR();
+                const int pr = *(volatile int *)&s_pz_pr;
+                EV_TR(3);
+                if (pr >= 0) {
+                    if (lane < 16) prefetch_l2(a.rowsum + (pr >> 8) * 256 + lane * 16);  // its chunk's row sums, for R2
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        pk[u] = a.rev[pr * REV_STRIDE + lane + 32 * u];
+                        fl[u] = a.nzflag[pr * REV_STRIDE + lane + 32 * u];
+                    }
+                }
+                // second half: the partner
+                while (*(volatile int *)&s_pz_req < ev_idx + 1) { }
+                KMC_CBAR();
+                const int pej = *(volatile int *)&s_pz_pej;
+                EV_TR(4);
+                if (pr >= 0 && pej >= 0) {
+                    if (lane < 16) prefetch_l2(a.rowsum + (pej >> 8) * 256 + lane * 16);
+#pragma unroll
+                    for (int u = 2; u < 4; ++u) {
+                        pk[u] = a.rev[pej * REV_STRIDE + lane + 32 * (u - 2)];
+                        fl[u] = a.nzflag[pej * REV_STRIDE + lane + 32 * (u - 2)];
+                    }
+                    int nrows = 0;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int rr = pk[u] >> 6;
+                        // (rows of this event's two sites are cleared entirely by this event's zero-out)
+                        const bool nz = pk[u] >= 0 && fl[u] == a.gen && rr != ri && rr != rj;
+                        s_pz_packed[nb][lane + 32 * u] = pk[u];
+                        s_pz_oldp[nb][lane + 32 * u] = nz ? 1.0 : 0.0;
+                        const bool loses = nz && rr != pr && rr != pej;
+                        const unsigned m = __ballot_sync(KMC_FULL_MASK, loses);
+                        if (loses) {
+                            s_pz_rows[nb][nrows + __popc(m & ((1u << lane) - 1u))] = rr;
+                            const double *rowp = a.prob + rr * nn;  // towards L2 for the next event's row sums
+                            prefetch_l2(rowp); prefetch_l2(rowp + 16); prefetch_l2(rowp + 32); prefetch_l2(rowp + nn - 1);
+                        }
+                        nrows += __popc(m);
+                    }
+                    EV_TR(5);
+                    if (lane == 0) { s_pz_nrows[nb] = nrows; s_pz_event[nb] = ev_idx + 1; }
+                }
+            }
         } else {
             // =============================== Z: zero-out ================================================================
             // zero_out_events_split (kmc_events.cu:247-266): every slot whose row or neighbour is i or j.  Padded slots
             // already hold rate 0 / NULL_EVENT, so rows i and j are cleared entirely; slots of other rows pointing at i / j
             // come from the reverse index.  4 warps (one per scheduler): the phase is two dependent round trips, not work.
-            if (ei >= 0 && tid < 2 * REV_STRIDE) {
-                const int s_site = (tid < REV_STRIDE) ? ei : ej;
-                const int q = tid & (REV_STRIDE - 1);
-                // the predictor staged this event's inputs during the previous event (it finished before barrier A)
-                const bool staged = s_rec[ev_idx & 1].fast && s_pz_event[ev_idx & 1] == ev_idx;
-                const int packed = staged ? s_pz_packed[ev_idx & 1][tid] : a.rev[s_site * REV_STRIDE + q];
-                if (q < nn) {  // the event's own rows
-                    const int sl = s_site * nn + q;
-                    a.prob[sl] = 0.0;
-                    a.type[sl] = KMCB200_NULL_EVENT;
-                }
-                if (q == 0) {  // ... whose sums become +0.0
-                    a.rowsum[s_site] = 0.0;
-                    const int c = s_site >> 8;
-                    const unsigned bit = 1u << (c & 31);
-                    if (!(atomicOr(&chunk_bits[c >> 5], bit) & bit)) {
-                        chunk_list[atomicAdd(&n_chunks, 1)] = c;
-                        if (atomicAdd(&super_cnt[c >> 8], 1) == 0) atomicAdd(&n_supers, 1);
-                    }
-                }
-                if (packed >= 0) {
-                    const int rr = packed >> 6;
-                    const int sl = rr * nn + (packed & 63);
-                    // a slot that already holds rate 0 does not change its row: only rows that lose a non-zero rate need
-                    // their sums repaired (their recomputed sums would be bit-identical anyway)
-                    const double oldp = staged ? s_pz_oldp[ev_idx & 1][tid] : a.prob[sl];
-                    a.type[sl] = KMCB200_NULL_EVENT;
-                    if (oldp != 0.0) {
+            // the housekeeping warp staged this event's zero-out inputs during the previous event, if it is the predicted one
+            const int zb = ev_idx & 1;
+            const bool staged = s_rec[zb].fast && s_pz_event[zb] == ev_idx;
+            if (staged) {
+                // ---- Z and R1 in one phase: the slots to clear and the rows that lose a rate are known, so the row sums do
+                // not wait for the zero-out's stores -- each warp clears "its" row's slots in registers
+                if (tid < 2 * REV_STRIDE) {
+                    const int s_site = (tid < REV_STRIDE) ? ei : ej;
+                    const int q = tid & (REV_STRIDE - 1);
+                    const int packed = s_pz_packed[zb][tid];
+                    if (q < nn) {  // the event's own rows
+                        const int sl = s_site * nn + q;
                         a.prob[sl] = 0.0;
-                        if (rr != ei && rr != ej) rows_list[atomicAdd(&n_rows, 1)] = rr;
+                        a.type[sl] = KMCB200_NULL_EVENT;
+                    }
+                    if (q == 0) {  // ... whose sums become +0.0
+                        a.rowsum[s_site] = 0.0;
+                        const int c = s_site >> 8;
+                        const unsigned bit = 1u << (c & 31);
+                        if (!(atomicOr(&chunk_bits[c >> 5], bit) & bit)) {
+                            chunk_list[atomicAdd(&n_chunks, 1)] = c;
+                            if (atomicAdd(&super_cnt[c >> 8], 1) == 0) atomicAdd(&n_supers, 1);
+                        }
+                    }
+                    if (packed >= 0) {
+                        const int sl = (packed >> 6) * nn + (packed & 63);
+                        a.type[sl] = KMCB200_NULL_EVENT;
+                        if (s_pz_oldp[zb][tid] != 0.0) {
+                            a.prob[sl] = 0.0;
+                            a.nzflag[s_site * REV_STRIDE + q] = 0;
+                        }
                     }
                 }
-            }
-            EV_TR(2);
-            asm volatile("bar.sync 1, %0;" ::"n"(NCW * 32) : "memory");  // ---- barrier B1 (the NCW working warps)
-            EV_TR(3);
-            EV_TICK(1);
-            // =============================== R1: row sums, one warp per row that lost a rate ===========================
-            // (a row listed twice -- it lost a rate to i and one to j -- is recomputed twice with the same result)
-            if (warp < NCW) {
-                const int nd = n_rows;
+                const int nd = s_pz_nrows[zb];
                 for (int qq = warp; qq < nd; qq += NCW) {
-                    const int rr = rows_list[qq];
+                    const int rr = s_pz_rows[zb][qq];
                     const int pb = rr * nn;
-                    const double p0 = (lane < nn) ? a.prob[pb + lane] : 0.0;
-                    const double p1 = (lane + 32 < nn) ? a.prob[pb + lane + 32] : 0.0;
+                    double p0 = (lane < nn) ? a.prob[pb + lane] : 0.0;
+                    double p1 = (lane + 32 < nn) ? a.prob[pb + lane + 32] : 0.0;
                     if (lane == 0) {  // dirty-chunk bookkeeping while the row is in flight
                         const int c = rr >> 8;
                         const unsigned bit = 1u << (c & 31);
@@ -1003,8 +1058,82 @@ __global__ void __launch_bounds__(EV_THREADS, 1) event_loop_kernel(EvLoopArgs a)
                             if (atomicAdd(&super_cnt[c >> 8], 1) == 0) atomicAdd(&n_supers, 1);
                         }
                     }
+                    // the slots of this row named by the two reverse-index rows (the row may be named by both)
+                    unsigned mlo = 0u, mhi = 0u;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int pk = s_pz_packed[zb][lane + 32 * u];
+                        if (pk >= 0 && (pk >> 6) == rr) {
+                            const int k = pk & 63;
+                            if (k < 32) mlo |= 1u << k; else mhi |= 1u << (k - 32);
+                        }
+                    }
+                    mlo = __reduce_or_sync(KMC_FULL_MASK, mlo);
+                    mhi = __reduce_or_sync(KMC_FULL_MASK, mhi);
+                    if ((mlo >> lane) & 1u) p0 = 0.0;
+                    if ((mhi >> lane) & 1u) p1 = 0.0;
                     const double sacc = warp_row_sum(p0, p1);
                     if (lane == 0) a.rowsum[rr] = sacc;
+                }
+            } else {
+                // (the chunks' row sums start their trip to L2 now: R2 reads them two phases later)
+                if (ei >= 0 && warp == NCW - 1) prefetch_l2(a.rowsum + (((lane < 16) ? ei : ej) >> 8) * 256 + (lane & 15) * 16);
+                if (ei >= 0 && tid < 2 * REV_STRIDE) {
+                    const int s_site = (tid < REV_STRIDE) ? ei : ej;
+                    const int q = tid & (REV_STRIDE - 1);
+                    const int packed = a.rev[s_site * REV_STRIDE + q];
+                    if (q < nn) {  // the event's own rows
+                        const int sl = s_site * nn + q;
+                        a.prob[sl] = 0.0;
+                        a.type[sl] = KMCB200_NULL_EVENT;
+                    }
+                    if (q == 0) {  // ... whose sums become +0.0
+                        a.rowsum[s_site] = 0.0;
+                        const int c = s_site >> 8;
+                        const unsigned bit = 1u << (c & 31);
+                        if (!(atomicOr(&chunk_bits[c >> 5], bit) & bit)) {
+                            chunk_list[atomicAdd(&n_chunks, 1)] = c;
+                            if (atomicAdd(&super_cnt[c >> 8], 1) == 0) atomicAdd(&n_supers, 1);
+                        }
+                    }
+                    if (packed >= 0) {
+                        const int rr = packed >> 6;
+                        const int sl = rr * nn + (packed & 63);
+                        // a slot that already holds rate 0 does not change its row: only rows that lose a non-zero rate need
+                        // their sums repaired (their recomputed sums would be bit-identical anyway)
+                        const double oldp = a.prob[sl];
+                        a.type[sl] = KMCB200_NULL_EVENT;
+                        if (oldp != 0.0) {
+                            a.prob[sl] = 0.0;
+                            a.nzflag[s_site * REV_STRIDE + q] = 0;
+                            if (rr != ei && rr != ej) rows_list[atomicAdd(&n_rows, 1)] = rr;
+                        }
+                    }
+                }
+                EV_TR(2);
+                asm volatile("bar.sync 1, %0;" ::"n"(NCW * 32) : "memory");  // ---- barrier B1 (the NCW working warps)
+                EV_TR(3);
+                EV_TICK(1);
+                // =============================== R1: row sums, one warp per row that lost a rate ===========================
+                // (a row listed twice -- it lost a rate to i and one to j -- is recomputed twice with the same result)
+                if (warp < NCW) {
+                    const int nd = n_rows;
+                    for (int qq = warp; qq < nd; qq += NCW) {
+                        const int rr = rows_list[qq];
+                        const int pb = rr * nn;
+                        const double p0 = (lane < nn) ? a.prob[pb + lane] : 0.0;
+                        const double p1 = (lane + 32 < nn) ? a.prob[pb + lane + 32] : 0.0;
+                        if (lane == 0) {  // dirty-chunk bookkeeping while the row is in flight
+                            const int c = rr >> 8;
+                            const unsigned bit = 1u << (c & 31);
+                            if (!(atomicOr(&chunk_bits[c >> 5], bit) & bit)) {
+                                chunk_list[atomicAdd(&n_chunks, 1)] = c;
+                                if (atomicAdd(&super_cnt[c >> 8], 1) == 0) atomicAdd(&n_supers, 1);
+                            }
+                        }
+                        const double sacc = warp_row_sum(p0, p1);
+                        if (lane == 0) a.rowsum[rr] = sacc;
+                    }
                 }
             }
             EV_TR(4);
@@ -1201,13 +1330,22 @@ extern "C" int kmcb200_events_create(kmcb200_ctx *ctx, int N, int nn, const int 
         kmcb200_events_destroy(ev);
         return KMCB200_E_CUDA;
     }
+    if (cudaMalloc((void **)&ev->revpos, (size_t)N * nn) != cudaSuccess ||
+        cudaMalloc((void **)&ev->nzflag, (size_t)N * REV_STRIDE) != cudaSuccess) {
+        kmc_set_error("cudaMalloc(reverse index flags) failed");
+        kmcb200_events_destroy(ev);
+        return KMCB200_E_CUDA;
+    }
+    cudaMemsetAsync(ev->revpos, 0xff, (size_t)N * nn, ctx->stream);
+    cudaMemsetAsync(ev->nzflag, 0, (size_t)N * REV_STRIDE, ctx->stream);
+    ev->gen = 0;
     cudaMemsetAsync(ev->rev, 0xff, (size_t)N * REV_STRIDE * sizeof(int), ctx->stream);
     cudaMemsetAsync(ev->rowsum, 0, (size_t)ev->nchunk * 256 * 2 * sizeof(double), ctx->stream);
     cudaMemsetAsync(ev->chunksum, 0, (size_t)ev->nsuper * 256 * sizeof(double), ctx->stream);
     cudaMemsetAsync(fill, 0, (size_t)(N + 2) * sizeof(int), ctx->stream);
     unsigned blocks = (unsigned)((total + 255) / 256);
     kmc_count_launch();
-    rev_fill_kernel<<<blocks, 256, 0, ctx->stream>>>(neigh, total, nn, fill, ev->rev, fill + N + 1);
+    rev_fill_kernel<<<blocks, 256, 0, ctx->stream>>>(neigh, total, nn, fill, ev->rev, ev->revpos, fill + N + 1);
     int ovf = 0;
     cudaMemcpyAsync(&ovf, fill + N + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
@@ -1229,7 +1367,7 @@ extern "C" int kmcb200_events_destroy(kmcb200_events *ev) {
     if (ev->ctx) cudaStreamSynchronize(ev->ctx->stream);
     cudaFree(ev->prob); cudaFree(ev->type); cudaFree(ev->rowsum); cudaFree(ev->chunksum); cudaFree(ev->supersum);
     cudaFree(ev->chunkincl);
-    cudaFree(ev->rev); cudaFree(ev->mt); cudaFree(ev->log); cudaFree(ev->log_psum);
+    cudaFree(ev->rev); cudaFree(ev->revpos); cudaFree(ev->nzflag); cudaFree(ev->mt); cudaFree(ev->log); cudaFree(ev->log_psum);
     cudaFree(ev->result);
     delete ev;
     return 0;
@@ -1302,11 +1440,16 @@ extern "C" int kmcb200_build_event_list(kmcb200_ctx *ctx, kmcb200_events *ev, in
     KMC_CHECK_ARG(ev->energies_set, "kmcb200_set_activation_energies was not called");
     const double kB = 8.617333262e-5;  // src/kmc_events.cu:5
     double kT = kB * T_bg;
+    if (++ev->gen > 255) {  // the generation stamps wrapped: expire every flag explicitly
+        KMC_CUDA(cudaMemsetAsync(ev->nzflag, 0, (size_t)N * REV_STRIDE, ctx->stream));
+        ev->gen = 1;
+    }
     kmc_count_launch();
     build_rates_kernel<<<(unsigned)ev->nchunk, 256, 0, ctx->stream>>>(N, nn, neigh, site_layer, kT, freq, sigma, k, x, y,
                                                                      z, site_potential_charge, site_element,
                                                                      site_charge, ev->energies, ev->prob, ev->type,
-                                                                     ev->rowsum, ev->chunksum, ev->rowincl);
+                                                                     ev->rowsum, ev->chunksum, ev->rowincl, ev->revpos,
+                                                                     ev->nzflag, ev->gen);
     KMC_CUDA(cudaGetLastError());
     kmc_count_launch();
     super_sums_kernel<<<(unsigned)ev->nsuper, 32, 0, ctx->stream>>>(ev->chunksum, ev->nchunk, ev->supersum,
@@ -1327,7 +1470,7 @@ extern "C" int kmcb200_execute_kmc_step(kmcb200_ctx *ctx, kmcb200_events *ev, in
     a.neigh = neigh; a.prob = ev->prob; a.type = ev->type;
     a.rowsum = ev->rowsum; a.chunksum = ev->chunksum; a.supersum = ev->supersum;
     a.rowincl = ev->rowincl; a.chunkincl = ev->chunkincl;
-    a.rev = ev->rev;
+    a.rev = ev->rev; a.revpos = ev->revpos; a.nzflag = ev->nzflag; a.gen = ev->gen;
     a.element = site_element; a.charge = site_charge;
     a.mt_state = ev->mt;
     a.inv_freq_threshold = 1 / freq;  // kmc_events.cu:448
