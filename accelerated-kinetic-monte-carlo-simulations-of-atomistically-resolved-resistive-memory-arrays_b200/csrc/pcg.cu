@@ -21,6 +21,7 @@ struct CgState {
 namespace {
 
 constexpr int CH = KMCB200_CHUNK;  // 256 rows per CTA == dot chunk
+constexpr int FIN_WIDE = 1024;     // threads of the 1-CTA dot finalize when it runs the two-level combine
 
 // "last CTA done" election (threadFenceReduction pattern).  Returns true in every thread of the last CTA.
 // remote: this CTA issued stores to peer memory that the elected CTA's flag must cover.
@@ -84,21 +85,54 @@ __device__ __forceinline__ void reduce_and_push_groups(const CommDev &cm, int sl
     for (int sidx = 0; sidx < nslots; ++sidx) {
         const double *part = cm.partials + (size_t)(slot0 + sidx) * cm.nchunks_global + cm.chunk_start;
         const size_t gbase = (size_t)(slot0 + sidx) * cm.ngroups_global + cm.group_start;
-        for (int g = w; g < local_groups; g += nw) {
-            const int c0 = g * KMCB200_DOT_GROUP + lane;
-            const double v0 = (c0 < local_chunks) ? __ldcg(part + c0) : 0.0;
-            const double v1 = (c0 + 32 < local_chunks) ? __ldcg(part + c0 + 32) : 0.0;
-            double tot = kmc_warp_xor_sum(v0);
-            tot = tot + kmc_warp_xor_sum(v1);
+        // two groups per trip: four loads in flight, four butterflies interleaved (the phase is latency, not work)
+        for (int g = w; g < local_groups; g += 2 * nw) {
+            const int g2 = g + nw;
+            const int c0 = g * KMCB200_DOT_GROUP + lane, d0 = g2 * KMCB200_DOT_GROUP + lane;
+            const bool two = g2 < local_groups;
+            double v0 = (c0 < local_chunks) ? __ldcg(part + c0) : 0.0;
+            double v1 = (c0 + 32 < local_chunks) ? __ldcg(part + c0 + 32) : 0.0;
+            double u0 = (two && d0 < local_chunks) ? __ldcg(part + d0) : 0.0;
+            double u1 = (two && d0 + 32 < local_chunks) ? __ldcg(part + d0 + 32) : 0.0;
 #pragma unroll
-            for (int q = 0; q < 6; ++q) tot = tot + 0.0;  // the six empty warps of chunk_reduce_256
+            for (int off = 16; off >= 1; off >>= 1) {
+                const double a0 = __shfl_xor_sync(KMC_FULL_MASK, v0, off), a1 = __shfl_xor_sync(KMC_FULL_MASK, v1, off);
+                const double b0 = __shfl_xor_sync(KMC_FULL_MASK, u0, off), b1 = __shfl_xor_sync(KMC_FULL_MASK, u1, off);
+                v0 = v0 + a0; v1 = v1 + a1; u0 = u0 + b0; u1 = u1 + b1;
+            }
+            double tot = v0 + v1, tot2 = u0 + u1;
+#pragma unroll
+            for (int q = 0; q < 6; ++q) { tot = tot + 0.0; tot2 = tot2 + 0.0; }  // the six empty warps of chunk_reduce_256
             if (lane == 0) {
                 cm.gtotals[gbase + g] = tot;
+                if (two) cm.gtotals[gbase + g2] = tot2;
                 for (int q = 0; q < cm.size; ++q)
-                    if (q != cm.rank) cm.peer_gtotals[q][gbase + g] = tot;
+                    if (q != cm.rank) {
+                        cm.peer_gtotals[q][gbase + g] = tot;
+                        if (two) cm.peer_gtotals[q][gbase + g2] = tot2;
+                    }
             }
         }
     }
+}
+// final_reduce when the CTA is wider than the spec's 256 threads: threads 0..255 reduce, every thread takes the barriers
+__device__ __forceinline__ double final_reduce_wide(const double *partials, long long n, double *sm) {
+    if (blockDim.x == CH) return kmc_final_reduce(partials, n, sm);
+    double acc = 0.0;
+    if (threadIdx.x < CH)
+        for (long long k = threadIdx.x; k < n; k += CH) acc = acc + __ldcg(partials + k);
+    acc = kmc_warp_xor_sum(acc);
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0 && w < 8) sm[w] = acc;
+    __syncthreads();
+    double r = 0.0;
+    if (threadIdx.x == 0) {
+        r = sm[0];
+#pragma unroll
+        for (int q = 1; q < 8; ++q) r = r + sm[q];
+    }
+    __syncthreads();
+    return r;
 }
 // completes `nslots` dot products at once: exchange (chunk partials for small systems, group totals for large ones), one
 // flag round trip, then the fixed-order reduction.  All threads of a 256-thread CTA; out[] valid in thread 0.
@@ -125,7 +159,7 @@ __device__ __forceinline__ void finish_dots(const CommDev &cm, int slot0, int ns
     }
     __syncthreads();
     for (int sidx = 0; sidx < nslots; ++sidx)
-        out[sidx] = kmc_final_reduce(cm.gtotals + (size_t)(slot0 + sidx) * cm.ngroups_global, cm.ngroups_global, red);
+        out[sidx] = final_reduce_wide(cm.gtotals + (size_t)(slot0 + sidx) * cm.ngroups_global, cm.ngroups_global, red);
 }
 // ---- completion of a dot product: exchange with the peers, reduce in the fixed order, update the PCG state.  Runs either
 // in the last CTA of the producing kernel (small problems: saves a launch) or in the 1-CTA dot_finalize_kernel (large
@@ -167,7 +201,8 @@ __device__ __forceinline__ void finish_init(const CommDev &cm, int local_chunks,
     }
 }
 // kind: 0 = p.Ap, 1 = r.z (+ iteration bookkeeping), 2 = setup (b.b and r.z)
-__global__ void __launch_bounds__(CH) dot_finalize_kernel(CommDev cm, int kind, int local_chunks, unsigned long long seq,
+// (launched with FIN_WIDE threads for the two-level combine -- 32 warps for the group level -- and CH otherwise)
+__global__ void __launch_bounds__(FIN_WIDE) dot_finalize_kernel(CommDev cm, int kind, int local_chunks, unsigned long long seq,
                                                          CgState *__restrict__ st) {
     __shared__ double red[8];
     if (kind != 2 && st->done) return;
@@ -655,7 +690,7 @@ extern "C" int kmcb200_spmv_dot(kmcb200_ctx *ctx, kmcb200_kmat *K, const double 
     KMC_TRY(spmv_launch(ctx, K, x_local, y_local, true, fuse, ds));
     if (!fuse) {
         kmc_count_launch();
-        dot_finalize_kernel<<<1, CH, 0, ctx->stream>>>(K->comm->dev, 0, nchunks, ds, st);
+        dot_finalize_kernel<<<1, K->comm->dev.group_chunks ? FIN_WIDE : CH, 0, ctx->stream>>>(K->comm->dev, 0, nchunks, ds, st);
         KMC_CUDA(cudaGetLastError());
     }
     if (dot_host) {
@@ -755,7 +790,7 @@ int kmc_pcg_run(kmcb200_ctx *ctx, kmcb200_kmat *K, const TunnelDev *tun, double 
         const unsigned long long ds = ++C->dot_seq;
         if (fuse) cg_init_kernel<true><<<eb, CH, 0, ctx->stream>>>(rows, (int)nchunks, r_local, K->Ap, diag_inv_local, K->z, C->dev, ds, st);
         else cg_init_kernel<false><<<eb, CH, 0, ctx->stream>>>(rows, (int)nchunks, r_local, K->Ap, diag_inv_local, K->z, C->dev, ds, st);
-        if (!fuse) { kmc_count_launch(); dot_finalize_kernel<<<1, CH, 0, ctx->stream>>>(C->dev, 2, (int)nchunks, ds, st); }
+        if (!fuse) { kmc_count_launch(); dot_finalize_kernel<<<1, C->dev.group_chunks ? FIN_WIDE : CH, 0, ctx->stream>>>(C->dev, 2, (int)nchunks, ds, st); }
     }
     KMC_CUDA(cudaGetLastError());
     int *h_flags = (int *)((char *)ctx->h_mail + 512);
@@ -799,7 +834,7 @@ int kmc_pcg_run(kmcb200_ctx *ctx, kmcb200_kmat *K, const TunnelDev *tun, double 
             if (!tun) {
                 const unsigned long long ds = ++C->dot_seq;
                 KMC_TRY(spmv_launch(ctx, K, C->dev.p_full[nb], K->Ap, true, fuse, ds));
-                if (!fuse) { kmc_count_launch(); dot_finalize_kernel<<<1, CH, 0, ctx->stream>>>(C->dev, 0, (int)nchunks, ds, st); }
+                if (!fuse) { kmc_count_launch(); dot_finalize_kernel<<<1, C->dev.group_chunks ? FIN_WIDE : CH, 0, ctx->stream>>>(C->dev, 0, (int)nchunks, ds, st); }
             } else {  // neighbour part, tunnel part, then p.Ap over the sum
                 const unsigned long long ds = ++C->dot_seq;
                 KMC_TRY(spmv_launch(ctx, K, C->dev.p_full[nb], K->Ap, false, 0, 0));
@@ -807,7 +842,7 @@ int kmc_pcg_run(kmcb200_ctx *ctx, kmcb200_kmat *K, const TunnelDev *tun, double 
                 kmc_count_launch();
                 if (fuse) cg_pap_kernel<true><<<eb, CH, 0, ctx->stream>>>(rows, (int)nchunks, C->dev.p_full[nb], K->Ap, C->dev, ds, st);
                 else cg_pap_kernel<false><<<eb, CH, 0, ctx->stream>>>(rows, (int)nchunks, C->dev.p_full[nb], K->Ap, C->dev, ds, st);
-                if (!fuse) { kmc_count_launch(); dot_finalize_kernel<<<1, CH, 0, ctx->stream>>>(C->dev, 0, (int)nchunks, ds, st); }
+                if (!fuse) { kmc_count_launch(); dot_finalize_kernel<<<1, C->dev.group_chunks ? FIN_WIDE : CH, 0, ctx->stream>>>(C->dev, 0, (int)nchunks, ds, st); }
             }
             if (rec) cudaEventRecord(pe[2], ctx->stream);
             kmc_count_launch();
@@ -819,7 +854,7 @@ int kmc_pcg_run(kmcb200_ctx *ctx, kmcb200_kmat *K, const TunnelDev *tun, double 
                 else
                     cg_update_kernel<false><<<eb, CH, 0, ctx->stream>>>(rows, (int)nchunks, C->dev.p_full[nb], K->Ap, diag_inv_local,
                                                                        x_local, r_local, K->z, C->dev, ds, st);
-                if (!fuse) { kmc_count_launch(); dot_finalize_kernel<<<1, CH, 0, ctx->stream>>>(C->dev, 1, (int)nchunks, ds, st); }
+                if (!fuse) { kmc_count_launch(); dot_finalize_kernel<<<1, C->dev.group_chunks ? FIN_WIDE : CH, 0, ctx->stream>>>(C->dev, 1, (int)nchunks, ds, st); }
             }
             if (rec) cudaEventRecord(pe[3], ctx->stream);
             launched_iters++;

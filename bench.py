@@ -499,13 +499,11 @@ def run_gpu(args):
             evp = json.load(open(os.path.join(PROFILES, "r2_event_loop.json")))
         except Exception:
             evp = {}
-        rt_ns = evp.get("dependent_round_trip_ns", 500.0)
-        n_rt = evp.get("dependent_round_trips_per_event", 5)
+        floor_us = evp.get("floor_us_per_event", 1.2)
         roof_ev = {"kernel": "event_loop_kernel (one persistent CTA; the residence-time loop of kmc_events.cu:448-516)",
                    "bound": "latency", "us_per_event": us_ev, "cycles_per_event": us_ev * sm_mhz,
                    "events_per_step": ev_per_step, "share_of_step": loop_ms / ms_per_step,
-                   "dependent_round_trips_per_event": n_rt, "round_trip_ns": rt_ns,
-                   "floor_us_per_event": n_rt * rt_ns * 1e-3, "frac": n_rt * rt_ns * 1e-3 / us_ev,
+                   "floor_us_per_event": floor_us, "floor_model": evp.get("floor_model"), "frac": floor_us / us_ev,
                    "dram_bytes_per_event": evp.get("dram_bytes_per_event"), "evidence": "profiles/r2_event_loop.md"}
 
     # ---- parity vs the oracle (rank 0; every GPU count) and the CPU baseline (N = 1), outside the timed region --------
