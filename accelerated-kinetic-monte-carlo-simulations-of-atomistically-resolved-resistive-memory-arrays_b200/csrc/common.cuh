@@ -70,6 +70,10 @@ struct kmcb200_ctx {
     bool smem_cfg_plan = false;
     double *partials = nullptr;   // device, 2 * max chunks
     size_t partials_cap = 0;
+    // persistent PCG loop kernel (pcg.cu): grid barrier counter + per-group arrival counters; co-resident CTAs per SM
+    void *pcg_loop_ws = nullptr;
+    size_t pcg_loop_ws_bytes = 0;
+    int pcg_loop_occ = 0;
 };
 
 int kmc_scratch(kmcb200_ctx *ctx, int slot, size_t bytes, void **out);

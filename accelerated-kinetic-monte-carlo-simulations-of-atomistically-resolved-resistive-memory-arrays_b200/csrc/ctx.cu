@@ -71,6 +71,7 @@ extern "C" int kmcb200_destroy(kmcb200_ctx *ctx) {
         if (b.ptr) cudaFree(b.ptr);
     if (ctx->cg_state) cudaFree(ctx->cg_state);
     if (ctx->partials) cudaFree(ctx->partials);
+    if (ctx->pcg_loop_ws) cudaFree(ctx->pcg_loop_ws);
     if (ctx->h_mail) cudaFreeHost(ctx->h_mail);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

@@ -479,6 +479,325 @@ __global__ void __launch_bounds__(CH) cg_update_kernel(int rows, int nchunks, co
     }
 }
 
+// ================================ the whole PCG loop as ONE persistent cooperative kernel =============================
+//   grid = as many 256-thread CTAs as are co-resident; a CTA walks the dot chunks c = blockIdx.x,
+// blockIdx.x + gridDim.x, ... in every phase.  Per iteration: p update (+ halo push) | grid barrier (+ halo flags) |
+// SpMV + p.Ap chunk partials | grid barrier (+ dot flags) | x, r, z update + r.z chunk partials | grid barrier (+ dot
+// flags).  The arithmetic, its order and the summation spec are those of the kernels above (same device functions), so
+// the iterates are bit-identical to the multi-kernel path and to the oracle.
+//  * two-level dots: the CTA that publishes the LAST chunk partial of a 64-chunk group (per-group counter) reduces the
+//    group, stores the total and pushes it to the peers; after the barrier EVERY CTA reduces the group totals itself, so
+//    alpha / beta / the convergence test are computed redundantly and identically everywhere -- no scalar broadcast.
+//  * every wait (grid barrier, peer flags) is bounded; a time-out raises CgState::comm_error and all CTAs leave.
+//  * the barrier's gpu-scope fence invalidates L1, so p entries written by other CTAs / peers are re-read from L2; the
+//    gathers use plain loads (not ld.global.nc: the vector changes during the kernel).
+struct PcgLoopArgs {
+    int rows, nchunks;
+    const int *row_ptr, *col;
+    const double *val, *dinv;
+    double *x, *r, *z, *Ap;
+    CgState *st;
+    unsigned long long *bar;   // grid barrier counter (zeroed by the host before the launch)
+    unsigned long long *work;  // chunk tickets of the SpMV phase (zeroed by the host before the launch)
+    unsigned long long *gdone; // group totals stored so far (monotone; zeroed by the host before the launch)
+    unsigned long long halo_seq0, dot_seq0;
+    unsigned long long *prof;  // KMCB200_PCG_LOOP_PROFILE: 8 accumulated phase times (ns) of CTA 0, else NULL
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// All threads of all CTAs call; returns false (in every thread of the CTA) when the wait timed out / the solve was aborted.
+// Two-level arrival (32 sub-counters, the last arrival of each goes on to the top counter) so that the arrivals do not
+// serialise on one L2 address; everybody spins on the top counter.  bar[0] = top, bar[16 + j] = sub-counter j (both
+// monotone over the whole solve).
+constexpr int BAR_SUB = 32;
+__device__ __forceinline__ bool grid_barrier(unsigned long long *bar, unsigned long long &gen, const CommDev &cm, int *sm_ok) {
+    __syncthreads();
+    ++gen;
+    if (threadIdx.x == 0) {
+        const unsigned nsub = gridDim.x < BAR_SUB ? gridDim.x : BAR_SUB;
+        const unsigned j = blockIdx.x % nsub;
+        const unsigned members = gridDim.x / nsub + (j < gridDim.x % nsub ? 1u : 0u);
+        __threadfence();
+        if (atomicAdd(bar + 16 + j, 1ull) + 1ull == gen * members) atomicAdd(bar, 1ull);
+        const unsigned long long target = gen * nsub;
+        int ok = 1;
+        unsigned spins = 0;
+        unsigned long long deadline = 0;
+        while (ld_acquire_gpu_u64(bar) < target) {
+            if ((++spins & 255u) == 0) {
+                const unsigned long long now = kmc_globaltimer_ns();
+                if (deadline == 0) deadline = now + cm.timeout_ns;
+                else if (now > deadline || *(volatile int *)cm.err) { *(volatile int *)cm.err = 1; ok = 0; break; }
+            }
+        }
+        __threadfence();
+        *sm_ok = ok;
+    }
+    __syncthreads();
+    return *sm_ok != 0;
+}
+// after a grid barrier: CTA 0 tells the peers that this rank's data of step `seq` is complete; every CTA waits for the
+// peers named in `mask`
+__device__ __forceinline__ bool peer_sync(const CommDev &cm, unsigned long long *const *peer_flags,
+                                          const unsigned long long *my_flags, unsigned mask, unsigned long long seq,
+                                          int *sm_ok) {
+    if (threadIdx.x == 0) {
+        if (blockIdx.x == 0) {
+            __threadfence_system();
+            for (int q = 0; q < cm.size; ++q)
+                if (q != cm.rank) kmc_store_relaxed_sys(peer_flags[q] + cm.rank, seq);
+        }
+        const bool ok = kmc_wait_flags(my_flags, mask, cm.rank, seq, cm.timeout_ns, cm.err);
+        __threadfence_system();
+        *sm_ok = ok ? 1 : 0;
+    }
+    __syncthreads();
+    return *sm_ok != 0;
+}
+// chunk partial of slot `slot`, published by thread 0 (no fence, no atomic in the hot phase: the grid barrier orders it)
+__device__ __forceinline__ void publish_chunk(const CommDev &cm, int slot, int c, double v) {
+    if (threadIdx.x == 0) {
+        const size_t idx = (size_t)slot * cm.nchunks_global + cm.chunk_start + c;
+        cm.partials[idx] = v;
+        if (cm.group_chunks == 0 && cm.size > 1) {
+            for (int q = 0; q < cm.size; ++q)
+                if (q != cm.rank) cm.peer_partials[q][idx] = v;
+            __threadfence_system();
+        }
+    }
+}
+// Group level of the two-level dot, after the grid barrier that made every chunk partial visible: warp w of CTA b reduces
+// group 8 b + w (spec: chunk_reduce_256 of the 64 partials padded with zeros), stores the total locally and at the peers and
+// counts it in; then EVERY CTA waits until all local groups are in (gdone is monotone: `expect` = groups x dot steps).
+__device__ __forceinline__ bool group_stage(const CommDev &cm, const PcgLoopArgs &a, int slot, int local_groups,
+                                            unsigned long long expect, int *sm_ok) {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int g = blockIdx.x * (CH / 32) + w; g < local_groups; g += gridDim.x * (CH / 32)) {
+        const double *part = cm.partials + (size_t)slot * cm.nchunks_global + cm.chunk_start;
+        const int c0 = g * KMCB200_DOT_GROUP + lane;
+        const double v0 = (c0 < a.nchunks) ? __ldcg(part + c0) : 0.0;
+        const double v1 = (c0 + 32 < a.nchunks) ? __ldcg(part + c0 + 32) : 0.0;
+        double tot = kmc_warp_xor_sum(v0);
+        tot = tot + kmc_warp_xor_sum(v1);
+#pragma unroll
+        for (int q = 0; q < 6; ++q) tot = tot + 0.0;  // the six empty warps of chunk_reduce_256
+        if (lane == 0) {
+            const size_t gi = (size_t)slot * cm.ngroups_global + cm.group_start + g;
+            cm.gtotals[gi] = tot;
+            if (cm.size > 1) {
+                for (int q = 0; q < cm.size; ++q)
+                    if (q != cm.rank) cm.peer_gtotals[q][gi] = tot;
+                __threadfence_system();
+            } else {
+                __threadfence();
+            }
+            atomicAdd(a.gdone, 1ull);
+        }
+    }
+    if (threadIdx.x == 0) {
+        int ok = 1;
+        unsigned spins = 0;
+        unsigned long long deadline = 0;
+        while (ld_acquire_gpu_u64(a.gdone) < expect) {
+            if ((++spins & 255u) == 0) {
+                const unsigned long long now = kmc_globaltimer_ns();
+                if (deadline == 0) deadline = now + cm.timeout_ns;
+                else if (now > deadline || *(volatile int *)cm.err) { *(volatile int *)cm.err = 1; ok = 0; break; }
+            }
+        }
+        *sm_ok = ok;
+    }
+    __syncthreads();
+    return *sm_ok != 0;
+}
+// the full dot product of slot `slot`, in every thread of the CTA (fixed-order reduction over all ranks' contributions)
+__device__ __forceinline__ double dot_total(const CommDev &cm, int slot, double *red, double *sm_bcast) {
+    double t;
+    if (cm.group_chunks) t = kmc_final_reduce(cm.gtotals + (size_t)slot * cm.ngroups_global, cm.ngroups_global, red);
+    else t = kmc_final_reduce(cm.partials + (size_t)slot * cm.nchunks_global, cm.nchunks_global, red);
+    if (threadIdx.x == 0) *sm_bcast = t;
+    __syncthreads();
+    t = *sm_bcast;
+    __syncthreads();
+    return t;
+}
+
+// One 256-row chunk of y = A p with the products p[row] * y[row] left in prod[] (row reduction spec of spmv_kernel).
+// Kept out of line: the loop then gets the 32-register allocation of the stand-alone SpMV (8 CTAs per SM) whatever the
+// persistent kernel keeps alive around it.
+template <int L, int DEPTH>
+__device__ __noinline__ void spmv_chunk_rows(const int *__restrict__ row_ptr, const int *__restrict__ col,
+                                             const double *__restrict__ val, const double *p, double *__restrict__ Ap,
+                                             int rows, int row0, int row_start, double *prod) {
+    constexpr int GROUPS = CH / L;
+    const int lane = threadIdx.x % L, grp = threadIdx.x / L;
+#pragma unroll 1
+    for (int pass = 0; pass < L; ++pass) {
+        const int rl = pass * GROUPS + grp;
+        const int r = row0 + rl;
+        double acc = 0.0;
+        if (r < rows) {
+            const int s = __ldg(row_ptr + r), e = __ldg(row_ptr + r + 1);
+            for (int k0 = s + lane; k0 < e; k0 += L * DEPTH) {
+                double v[DEPTH], xv[DEPTH];
+                int cc[DEPTH];
+#pragma unroll
+                for (int t = 0; t < DEPTH; ++t) {
+                    const int kk = k0 + t * L;
+                    const bool in = kk < e;
+                    v[t] = in ? __ldcs(val + kk) : 0.0;
+                    cc[t] = in ? __ldcs(col + kk) : -1;
+                }
+#pragma unroll
+                for (int t = 0; t < DEPTH; ++t) xv[t] = (cc[t] >= 0) ? p[cc[t]] : 0.0;
+#pragma unroll
+                for (int t = 0; t < DEPTH; ++t)
+                    if (cc[t] >= 0) acc = fma(v[t], xv[t], acc);
+            }
+        }
+#pragma unroll
+        for (int off = L / 2; off >= 1; off >>= 1) acc = acc + __shfl_xor_sync(KMC_FULL_MASK, acc, off);
+        if (lane == 0) {
+            double pv = 0.0;
+            if (r < rows) {
+                __stcs(Ap + r, acc);
+                pv = p[row_start + r] * acc;
+            }
+            prod[rl] = pv;
+        }
+    }
+}
+
+template <int L, int DEPTH>
+__global__ void __launch_bounds__(CH, 8) pcg_loop_kernel(PcgLoopArgs a, CommDev cm) {
+    __shared__ double prod[CH];
+    __shared__ double red[8];
+    __shared__ double bcast;
+    __shared__ int okf, s_chunk;
+    long long nxt = 0;
+    unsigned long long tbase = 0;
+    CgState *st = a.st;
+    if (st->done) return;  // converged at setup (uniform: every CTA reads the same word)
+    const int local_groups = cm.group_chunks ? (a.nchunks + KMCB200_DOT_GROUP - 1) / KMCB200_DOT_GROUP : 0;
+    const double bb = st->bb, tol2 = st->tol2;
+    const int max_it = st->max_it;
+    double rz = st->rz, rz_old = st->rz_old, pAp = 0.0;
+    int k = st->k;
+    unsigned long long target = 0, gsteps = 0, hs = a.halo_seq0, ds = a.dot_seq0;
+    const unsigned all_peers = (cm.size >= 32 ? 0xffffffffu : ((1u << cm.size) - 1u));
+    bool ok = true;
+    const bool prof = a.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+    unsigned long long tp = prof ? kmc_globaltimer_ns() : 0;
+#define PCG_TICK(q) do { if (prof) { const unsigned long long n_ = kmc_globaltimer_ns(); a.prof[q] += n_ - tp; tp = n_; } } while (0)
+    while (true) {
+        // ---------------- p = z (k == 1)  or  p = z + (rz / rz_old) p ; halo push -----------------------------------
+        ++hs;
+        const int nb = (int)(hs & 1);
+        const double *p_old = cm.p_full[nb ^ 1];
+        double *p_new = cm.p_full[nb];
+        const bool first = (k == 1);
+        const double beta = first ? 0.0 : rz / rz_old;
+        for (int c = blockIdx.x; c < a.nchunks; c += gridDim.x) {
+            const int i = c * CH + threadIdx.x;
+            if (i < a.rows) {
+                const int g = cm.row_start + i;
+                double v;
+                // streaming (evict-first) accesses for everything but p: only the new p must stay L2 resident for the gathers
+                if (first) {
+                    v = __ldcs(a.z + i);
+                } else {
+                    const double t = beta * __ldcs(p_old + g);
+                    v = __ldcs(a.z + i) + t;
+                }
+                p_new[g] = v;
+                if (cm.size > 1) {
+                    unsigned m = cm.send_mask[i];
+                    while (m) {
+                        const int q = __ffs(m) - 1;
+                        m &= m - 1;
+                        cm.peer_p_full[q][nb][g] = v;
+                    }
+                }
+            }
+        }
+        if (cm.size > 1) __threadfence_system();
+        PCG_TICK(0);
+        ok = grid_barrier(a.bar, target, cm, &okf);
+        if (ok && cm.size > 1) ok = peer_sync(cm, cm.peer_flag_halo, cm.flag_halo, cm.recv_mask, hs, &okf);
+        if (!ok) break;
+        PCG_TICK(1);
+        // ---------------- Ap = A p ; p.Ap ---------------------------------------------------------------------------
+        ++ds;
+        // chunks are handed out by ticket (the hardware scheduler's balancing, kept): each CTA takes tickets until it draws
+        // one past the end, so an iteration consumes exactly nchunks + gridDim.x of them; the next ticket is drawn while
+        // the current chunk is processed
+        if (threadIdx.x == 0) nxt = (long long)atomicAdd(a.work, 1ull) - (long long)tbase;
+        while (true) {
+            if (threadIdx.x == 0) s_chunk = (int)(nxt < (long long)a.nchunks ? nxt : (long long)a.nchunks);
+            __syncthreads();
+            const int c = s_chunk;
+            if (c >= a.nchunks) break;
+            if (threadIdx.x == 0) nxt = (long long)atomicAdd(a.work, 1ull) - (long long)tbase;
+            spmv_chunk_rows<L, DEPTH>(a.row_ptr, a.col, a.val, p_new, a.Ap, a.rows, c * CH, cm.row_start, prod);
+            __syncthreads();
+            const double cpart = kmc_chunk_reduce_256(prod[threadIdx.x], red);
+            publish_chunk(cm, 0, c, cpart);
+        }
+        tbase += (unsigned long long)a.nchunks + gridDim.x;
+        PCG_TICK(2);
+        ok = grid_barrier(a.bar, target, cm, &okf);
+        if (ok && local_groups) ok = group_stage(cm, a, 0, local_groups, (gsteps += (unsigned long long)local_groups), &okf);
+        if (ok && cm.size > 1) ok = peer_sync(cm, cm.peer_flag_dot, cm.flag_dot, all_peers, ds, &okf);
+        if (!ok) break;
+        PCG_TICK(3);
+        pAp = dot_total(cm, 0, red, &bcast);
+        PCG_TICK(4);
+        // ---------------- x += a p ; r -= a Ap ; z = M^-1 r ; r.z ---------------------------------------------------
+        ++ds;
+        const double al = rz / pAp, nal = -al;
+        for (int c = blockIdx.x; c < a.nchunks; c += gridDim.x) {
+            const int i = c * CH + threadIdx.x;
+            double v = 0.0;
+            if (i < a.rows) {
+                const double pi = p_new[cm.row_start + i];
+                const double xi = fma(al, pi, __ldcs(a.x + i));
+                const double ri = fma(nal, __ldcs(a.Ap + i), __ldcs(a.r + i));
+                const double zi = ri * __ldcs(a.dinv + i);
+                __stcs(a.x + i, xi);
+                __stcs(a.r + i, ri);
+                __stcs(a.z + i, zi);
+                v = ri * zi;
+            }
+            const double cpart = kmc_chunk_reduce_256(v, red);
+            publish_chunk(cm, 1, c, cpart);
+        }
+        PCG_TICK(5);
+        ok = grid_barrier(a.bar, target, cm, &okf);
+        if (ok && local_groups) ok = group_stage(cm, a, 1, local_groups, (gsteps += (unsigned long long)local_groups), &okf);
+        if (ok && cm.size > 1) ok = peer_sync(cm, cm.peer_flag_dot, cm.flag_dot, all_peers, ds, &okf);
+        if (!ok) break;
+        PCG_TICK(6);
+        rz_old = rz;
+        rz = dot_total(cm, 1, red, &bcast);
+        PCG_TICK(7);
+        ++k;
+        if (!(rz / bb > tol2 && k <= max_it)) break;
+    }
+#undef PCG_TICK
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        st->rz = rz;
+        st->rz_old = rz_old;
+        st->pAp = pAp;
+        st->k = k;
+        st->iters = k - 1;
+        st->done = 1;
+    }
+}
+
 // ---- split-sparse extension (reference dist_iterative/dist_spmv_split_sparse.cpp:5-79, spmm_split_sparse1):
 // Ap += scatter(T_tunnel * gather(p)).  One warp per local tunnel row; row reduction spec with 32 lanes (lane l takes
 // entries l, l+32, ... with fma in increasing k, then the xor butterfly 16..1); the gather reads p through the
@@ -793,6 +1112,47 @@ int kmc_pcg_run(kmcb200_ctx *ctx, kmcb200_kmat *K, const TunnelDev *tun, double 
         if (!fuse) { kmc_count_launch(); dot_finalize_kernel<<<1, C->dev.group_chunks ? FIN_WIDE : CH, 0, ctx->stream>>>(C->dev, 2, (int)nchunks, ds, st); }
     }
     KMC_CUDA(cudaGetLastError());
+    // ---- the iterations: the multi-kernel loop below (default), or ONE persistent cooperative kernel
+    // (KMCB200_PCG_PERSISTENT=1; not for the tunnel operator).  Measured on one B200 at 2.3 M rows: 254 vs 226 us per
+    // iteration -- see DESIGN.md 10.1 for why the persistent form loses there.
+    const bool want_persist = getenv("KMCB200_PCG_PERSISTENT") != nullptr && atoi(getenv("KMCB200_PCG_PERSISTENT")) != 0 &&
+                              getenv("KMCB200_PCG_PROFILE") == nullptr;  // (read per call: the tests switch it)
+    const bool persistent = !tun && want_persist;
+    if (persistent) {
+        constexpr int L = KMCB200_SPMV_LANES;
+        if (ctx->pcg_loop_occ == 0) {
+            int occ = 0;
+            KMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pcg_loop_kernel<L, 4>, CH, 0));
+            ctx->pcg_loop_occ = occ > 0 ? occ : -1;
+        }
+        if (ctx->pcg_loop_occ < 0) { kmc_set_error("pcg_loop_kernel does not fit on an SM"); return KMCB200_E_CUDA; }
+        const size_t ws = 64 * sizeof(unsigned long long);  // [0] barrier top, [1] tickets, [2] groups done, [8..15] profile, [16..47] barrier sub-counters
+        if (ctx->pcg_loop_ws_bytes < ws) {
+            if (ctx->pcg_loop_ws) { KMC_CUDA(cudaStreamSynchronize(ctx->stream)); KMC_CUDA(cudaFree(ctx->pcg_loop_ws)); }
+            KMC_CUDA(cudaMalloc(&ctx->pcg_loop_ws, ws));
+            ctx->pcg_loop_ws_bytes = ws;
+        }
+        KMC_CUDA(cudaMemsetAsync(ctx->pcg_loop_ws, 0, ws, ctx->stream));
+        // as many CTAs as are co-resident, trimmed so that every CTA walks the same number of chunks (+- 1)
+        const unsigned max_grid = (unsigned)(ctx->pcg_loop_occ * ctx->sm_count);
+        const unsigned per = (nchunks + max_grid - 1) / max_grid;
+        const unsigned grid = per ? (nchunks + per - 1) / per : 1;
+        PcgLoopArgs a;
+        a.rows = rows; a.nchunks = (int)nchunks;
+        a.row_ptr = K->row_ptr; a.col = K->col; a.val = K->val; a.dinv = diag_inv_local;
+        a.x = x_local; a.r = r_local; a.z = K->z; a.Ap = K->Ap;
+        a.st = st;
+        a.bar = (unsigned long long *)ctx->pcg_loop_ws;
+        a.work = (unsigned long long *)ctx->pcg_loop_ws + 1;
+        a.gdone = (unsigned long long *)ctx->pcg_loop_ws + 2;
+        static const bool loop_prof = getenv("KMCB200_PCG_LOOP_PROFILE") != nullptr;
+        a.prof = loop_prof ? (unsigned long long *)((char *)ctx->pcg_loop_ws + 64) : nullptr;
+        a.halo_seq0 = C->halo_seq; a.dot_seq0 = C->dot_seq;
+        CommDev cmv = C->dev;
+        void *kargs[] = {&a, &cmv};
+        kmc_count_launch();
+        KMC_CUDA(cudaLaunchCooperativeKernel((const void *)pcg_loop_kernel<L, 4>, dim3(grid ? grid : 1), dim3(CH), kargs, 0, ctx->stream));
+    }
     int *h_flags = (int *)((char *)ctx->h_mail + 512);
     auto read_flags = [&]() -> int {
         KMC_CUDA(cudaMemcpyAsync(h_flags, &st->k, 5 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -805,6 +1165,18 @@ int kmc_pcg_run(kmcb200_ctx *ctx, kmcb200_kmat *K, const TunnelDev *tun, double 
         return 0;
     };
     KMC_TRY(read_flags());
+    if (persistent) {  // the kernel ran h_flags[3] iterations: one halo step and two dot steps each, on every rank
+        C->halo_seq += (unsigned long long)h_flags[3];
+        C->dot_seq += 2ull * (unsigned long long)h_flags[3];
+        if (getenv("KMCB200_PCG_LOOP_PROFILE") && h_flags[3] > 0) {
+            unsigned long long pr[8];
+            cudaMemcpy(pr, (char *)ctx->pcg_loop_ws + 64, sizeof(pr), cudaMemcpyDeviceToHost);
+            fprintf(stderr, "[pcg loop] rank %d rows %d, %d iterations, us/iteration of CTA 0: p-update %.1f | barrier %.1f | spmv %.1f | barrier %.1f | "
+                            "dot %.1f | update %.1f | barrier %.1f | dot %.1f\n", C->rank, rows, h_flags[3],
+                    pr[0] * 1e-3 / h_flags[3], pr[1] * 1e-3 / h_flags[3], pr[2] * 1e-3 / h_flags[3], pr[3] * 1e-3 / h_flags[3],
+                    pr[4] * 1e-3 / h_flags[3], pr[5] * 1e-3 / h_flags[3], pr[6] * 1e-3 / h_flags[3], pr[7] * 1e-3 / h_flags[3]);
+        }
+    }
     int batch = 4;
     // KMCB200_PCG_PROFILE=1: CUDA events around every kernel of the iteration (diagnostics only; serialises nothing
     // by itself, the events sit on the same stream)

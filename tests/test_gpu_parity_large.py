@@ -93,11 +93,28 @@ def test_highvac3x3_brick_supersteps_vs_oracle(kmc, ctx, orc):
     assert seen[kmc.VACANCY_GENERATION] > 0 and seen[kmc.VACANCY_RECOMBINATION] > 0
 
 
-def test_sharded_solve_two_processes_vs_oracle(kmc, tmp_path):
+def test_persistent_pcg_kernel_vs_oracle(kmc, ctx, orc):
+    """The opt-in one-kernel PCG loop (pcg_loop_kernel: grid barriers, ticketed chunks, group stage after the barrier,
+    KMCB200_PCG_PERSISTENT=1) against the ORACLE on the 4x4 stand-in: same iteration count, boundary potential bit for bit."""
+    s = _standin(kmc, 4, Vd=15.0, rnd_seed=32)
+    old = os.environ.get("KMCB200_PCG_PERSISTENT")
+    os.environ["KMCB200_PCG_PERSISTENT"] = "1"
+    try:
+        _check_supersteps(kmc, ctx, orc, s, 2)
+    finally:
+        if old is None:
+            os.environ.pop("KMCB200_PCG_PERSISTENT", None)
+        else:
+            os.environ["KMCB200_PCG_PERSISTENT"] = old
+
+
+@pytest.mark.parametrize("persistent", ["0", "1"])
+def test_sharded_solve_two_processes_vs_oracle(kmc, tmp_path, persistent):
     """Row-sharded K solve + sharded Coulomb sum on 2 ranks against the ORACLE, on the kernel paths
     bench.py runs at N > 1: 4x4 stand-in = 2 282 dot chunks -> FUSE=false kernels + dot_finalize with the two-level
     (group-total) exchange, halo pushes, NVLink all-gather of the potentials.  Driven through the C ABI only (file
-    rendezvous + CUDA IPC, no NCCL), so both ranks can share GPU 0 on a one-GPU box: the test never skips."""
+    rendezvous + CUDA IPC, no NCCL), so both ranks can share GPU 0 on a one-GPU box: the test never skips.
+    persistent = "1": the same with the opt-in one-kernel PCG loop (grid barriers + peer flags inside the kernel)."""
     import json
     import subprocess
     import sys
@@ -106,7 +123,8 @@ def test_sharded_solve_two_processes_vs_oracle(kmc, tmp_path):
     worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "mgpu_cabi_worker.py")
     procs = [subprocess.Popen([sys.executable, worker, str(r), "2", str(tmp_path / "rdv"), str(r if ngpu >= 2 else 0), "4"],
                               stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
-                              env=dict(os.environ, KMCB200_COMM_TIMEOUT_MS="120000")) for r in range(2)]
+                              env=dict(os.environ, KMCB200_COMM_TIMEOUT_MS="120000", KMCB200_PCG_PERSISTENT=persistent))
+             for r in range(2)]
     outs = [p.communicate(timeout=1500) for p in procs]
     reps = []
     for p, (so, se) in zip(procs, outs):
