@@ -4,6 +4,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+
 #include "comm.cuh"
 #include "kmat.cuh"
 
@@ -41,6 +43,14 @@ __global__ void recv_mask_kernel(int n_global, const unsigned char *__restrict__
     atomicOr(mask_out, 1u << q);
 }
 
+// appends every global row j with my_need[j] to the list (order fixed afterwards by a host-side sort: setup only)
+__global__ void halo_list_kernel(int n_global, const unsigned char *__restrict__ my_need, int *__restrict__ list,
+                                 int *__restrict__ count) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_global || !my_need[j]) return;
+    list[atomicAdd(count, 1)] = j;
+}
+
 int comm_alloc(kmcb200_comm *c) {
     const size_t n = (size_t)c->n_global;
     size_t off = 0;
@@ -53,6 +63,11 @@ int comm_alloc(kmcb200_comm *c) {
     c->off_flag_gather = off; off += 256;
     c->off_flag_ack = off; off += 256;
     c->off_gather = off; off = align_up(off + (size_t)(c->gather_cap + 1) * sizeof(double), 256);
+    if (c->size > 1) {  // fence-free dot cells + z halo landing zone (comm.cuh)
+        const size_t ll_vals = c->group_chunks ? c->ngroups_global : c->nchunks_global;
+        c->off_ll = off; off = align_up(off + 4 * (ll_vals + 1) * sizeof(uint4), 256);
+        c->off_z = off; off = align_up(off + n * sizeof(double), 256);
+    }
     c->arena_bytes = align_up(off, 2 << 20);
     KMC_CUDA(cudaMalloc((void **)&c->arena, c->arena_bytes));
     KMC_CUDA(cudaMemsetAsync(c->arena, 0, c->arena_bytes, c->ctx->stream));
@@ -86,6 +101,15 @@ void kmc_comm_fill_dev(kmcb200_comm *c) {
     d.flag_dot = (unsigned long long *)(c->arena + c->off_flag_dot);
     d.flag_halo = (unsigned long long *)(c->arena + c->off_flag_halo);
     d.gather = (double *)(c->arena + c->off_gather);
+    {
+        static const bool ll_env = !(getenv("KMCB200_COMM_LL") && atoi(getenv("KMCB200_COMM_LL")) == 0);
+        d.ll_mode = (c->size > 1 && ll_env) ? 1 : 0;
+    }
+    d.ll_vals = c->group_chunks ? c->ngroups_global : c->nchunks_global;
+    d.ll = c->size > 1 ? (uint4 *)(c->arena + c->off_ll) : nullptr;
+    d.z_full = c->size > 1 ? (double *)(c->arena + c->off_z) : nullptr;
+    d.halo_rows = c->halo_rows;
+    d.nhalo = c->nhalo;
     d.flag_gather = (unsigned long long *)(c->arena + c->off_flag_gather);
     d.flag_ack = (unsigned long long *)(c->arena + c->off_flag_ack);
     for (int q = 0; q < KMC_MAX_RANKS; ++q) {
@@ -97,6 +121,8 @@ void kmc_comm_fill_dev(kmcb200_comm *c) {
         d.peer_flag_dot[q] = base ? (unsigned long long *)(base + c->off_flag_dot) : nullptr;
         d.peer_flag_halo[q] = base ? (unsigned long long *)(base + c->off_flag_halo) : nullptr;
         d.peer_gather[q] = base ? (const double *)(base + c->off_gather) : nullptr;
+        d.peer_ll[q] = (base && c->size > 1) ? (uint4 *)(base + c->off_ll) : nullptr;
+        d.peer_z_full[q] = (base && c->size > 1) ? (double *)(base + c->off_z) : nullptr;
         d.peer_flag_gather[q] = base ? (unsigned long long *)(base + c->off_flag_gather) : nullptr;
         d.peer_flag_ack[q] = base ? (unsigned long long *)(base + c->off_flag_ack) : nullptr;
     }
@@ -155,6 +181,7 @@ extern "C" int kmcb200_comm_destroy(kmcb200_comm *c) {
         if (q != c->rank && c->peer_arena[q]) cudaIpcCloseMemHandle(c->peer_arena[q]);
     cudaFree(c->arena);
     cudaFree(c->send_mask);
+    cudaFree(c->halo_rows);
     cudaFree(c->err_word);
     delete c;
     return 0;
@@ -228,6 +255,25 @@ extern "C" int kmcb200_comm_set_send_masks(kmcb200_comm *c, const unsigned char 
     KMC_CUDA(cudaMemcpyAsync(&m, d_mask, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
     KMC_CUDA(cudaStreamSynchronize(ctx->stream));
     c->recv_mask = m & ~(1u << c->rank);
+    {   // the halo rows of this rank (global ids, ascending): the p-update forms their p entries locally (comm.cuh)
+        int *d_list = nullptr, *d_count = (int *)(d_mask + 32);
+        KMC_TRY(kmc_scratch(ctx, 6, (size_t)c->n_global * sizeof(int) + 16, (void **)&d_list));
+        KMC_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int), ctx->stream));
+        kmc_count_launch();
+        halo_list_kernel<<<(c->n_global + 255) / 256, 256, 0, ctx->stream>>>(c->n_global, all_need_dev + (size_t)c->rank * c->n_global,
+                                                                            d_list, d_count);
+        KMC_CUDA(cudaGetLastError());
+        int cnt = 0;
+        KMC_CUDA(cudaMemcpyAsync(&cnt, d_count, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        KMC_CUDA(cudaStreamSynchronize(ctx->stream));
+        std::vector<int> h((size_t)cnt);
+        if (cnt > 0) KMC_CUDA(cudaMemcpy(h.data(), d_list, (size_t)cnt * sizeof(int), cudaMemcpyDeviceToHost));
+        std::sort(h.begin(), h.end());
+        if (c->halo_rows) { KMC_CUDA(cudaFree(c->halo_rows)); c->halo_rows = nullptr; }
+        KMC_CUDA(cudaMalloc((void **)&c->halo_rows, ((size_t)cnt + 1) * sizeof(int)));
+        if (cnt > 0) KMC_CUDA(cudaMemcpy(c->halo_rows, h.data(), (size_t)cnt * sizeof(int), cudaMemcpyHostToDevice));
+        c->nhalo = cnt;
+    }
     c->masks_set = true;
     kmc_comm_fill_dev(c);
     return 0;

@@ -44,6 +44,22 @@ struct CommDev {
     unsigned long long *peer_flag_gather[KMC_MAX_RANKS], *peer_flag_ack[KMC_MAX_RANKS];
     unsigned long long timeout_ns;   // bound of every peer-flag wait
     int *err;                        // device word raised when a wait timed out (CgState::comm_error of the context)
+    // ---- PCG loop at size > 1 (ll_mode, the default): two exchanges per iteration instead of three, none with a fence
+    // on its critical path.  (1) The kernels that compute z (setup, x/r/z update) store the z entries a peer's matrix
+    // block references straight into that peer's z_full and fence them before they end; every rank then forms the halo
+    // entries of p = z + beta p itself (same operands, same operations => same bits), so p needs no exchange.  (2) Dot
+    // contributions travel as 16-byte {lo, seq, hi, seq} cells (each 8-byte half carries its own sequence number, so the
+    // receiver needs no flag and neither side a fence); cells are double buffered by the parity of the sequence number.
+    // A peer's cells of dot s arrive after its z stores of the same step were fenced, so "all cells of r.z present"
+    // implies "all z halo entries present".
+    int ll_mode;
+    int ll_vals;                          // cells per dot: nchunks_global (single-level combine) or ngroups_global
+    uint4 *ll;                            // local, [2][2][ll_vals]
+    uint4 *peer_ll[KMC_MAX_RANKS];
+    double *z_full;                       // local, indexed by global row; only halo entries are ever written (by peers)
+    double *peer_z_full[KMC_MAX_RANKS];
+    const int *halo_rows;                 // global rows this rank's matrix block reads from peers, ascending
+    int nhalo;
 };
 
 struct kmcb200_comm {
@@ -54,7 +70,9 @@ struct kmcb200_comm {
     char *arena = nullptr;  // local allocation shared with the peers through CUDA IPC
     size_t arena_bytes = 0;
     size_t off_p[2] = {0, 0}, off_partials = 0, off_gtotals = 0, off_flag_dot = 0, off_flag_halo = 0;
-    size_t off_gather = 0, off_flag_gather = 0, off_flag_ack = 0;
+    size_t off_gather = 0, off_flag_gather = 0, off_flag_ack = 0, off_ll = 0, off_z = 0;
+    int *halo_rows = nullptr;  // device, nhalo entries (built by kmcb200_comm_set_send_masks)
+    int nhalo = 0;
     long long gather_cap = 0;          // doubles in the all-gather staging region
     unsigned long long gather_seq = 0;  // host-side call counter (identical on every rank)
     int *err_word = nullptr;            // device int raised by a timed-out wait outside a PCG solve
@@ -82,6 +100,20 @@ __device__ __forceinline__ unsigned long long kmc_load_relaxed_sys(const unsigne
     unsigned long long v;
     asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
+}
+// 16-byte cell of the fence-free dot exchange (the LL idea of NCCL: data and sequence number share an 8-byte store)
+__device__ __forceinline__ void kmc_ll_store(uint4 *cell, double v, unsigned seq32) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(cell), "r"((unsigned)b), "r"(seq32),
+                 "r"((unsigned)(b >> 32)), "r"(seq32)
+                 : "memory");
+}
+__device__ __forceinline__ bool kmc_ll_try_load(const uint4 *cell, unsigned seq32, double *v) {
+    unsigned a, fa, b, fb;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(fa), "=r"(b), "=r"(fb) : "l"(cell) : "memory");
+    if (fa != seq32 || fb != seq32) return false;
+    *v = __longlong_as_double((long long)(((unsigned long long)b << 32) | a));
+    return true;
 }
 __device__ __forceinline__ unsigned long long kmc_globaltimer_ns() {
     unsigned long long t;

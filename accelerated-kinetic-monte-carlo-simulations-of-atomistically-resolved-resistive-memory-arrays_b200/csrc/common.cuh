@@ -137,6 +137,29 @@ __device__ __forceinline__ bool kmc_possibly_charged(int el) {
     return el == KMCB200_OXYGEN_DEFECT || el == KMCB200_O || el == KMCB200_VACANCY || el == KMCB200_DEFECT;
 }
 
+// Programmatic dependent launch (PDL): a kernel launched with kmc_launch_pdl may become resident while its predecessor
+// on the stream is still draining; it must call kmc_pdl_wait() before it touches anything the predecessor reads or
+// writes (the wait returns once the predecessor grid has completed and its stores are visible; it is a no-op for an
+// ordinary launch).  kmc_pdl_trigger() lets the NEXT kernel on the stream start its own launch as soon as every CTA of
+// this grid has started.  Only the launch latency and the CTA ramp-up overlap; all data accesses stay ordered.
+__device__ __forceinline__ void kmc_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void kmc_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+static inline cudaError_t kmc_launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem,
+                                         cudaStream_t stream, bool pdl, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl ? 1u : 0u;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // summation spec: 32-lane butterfly, every lane ends with the same value
 __device__ __forceinline__ double kmc_warp_xor_sum(double v) {
 #pragma unroll

@@ -136,8 +136,99 @@ __device__ __forceinline__ double final_reduce_wide(const double *partials, long
 }
 // completes `nslots` dot products at once: exchange (chunk partials for small systems, group totals for large ones), one
 // flag round trip, then the fixed-order reduction.  All threads of a 256-thread CTA; out[] valid in thread 0.
+// ---- the same completion with the fence-free exchange (CommDev::ll_mode): this rank's contributions (chunk partials of a
+// single-level system, group totals otherwise) are stored as {lo, seq, hi, seq} cells into every peer's cell array, then
+// the cells of all other ranks' index ranges are polled out of the local cell array into the plain table the fixed-order
+// reduction reads.  No flag, no fence: a cell is valid as soon as both halves carry this dot's sequence number.
+__device__ __forceinline__ void finish_dots_ll(const CommDev &cm, int slot0, int nslots, int local_chunks,
+                                               unsigned long long seq, double *red, double *out) {
+    const bool grp = cm.group_chunks != 0;
+    const unsigned s32 = (unsigned)seq;
+    const int nglob = cm.ll_vals;
+    const int nloc = grp ? (local_chunks + KMCB200_DOT_GROUP - 1) / KMCB200_DOT_GROUP : local_chunks;
+    const int first = grp ? cm.group_start : cm.chunk_start;
+    double *table = grp ? cm.gtotals : cm.partials;
+    const int tstride = grp ? cm.ngroups_global : cm.nchunks_global;
+    const size_t cell0 = (size_t)(seq & 1ull) * 2u * (size_t)nglob;
+    if (grp) {
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        for (int sidx = 0; sidx < nslots; ++sidx) {
+            const double *part = cm.partials + (size_t)(slot0 + sidx) * cm.nchunks_global + cm.chunk_start;
+            // two groups per trip: four loads in flight, four butterflies interleaved (the phase is latency, not work)
+            for (int g = w; g < nloc; g += 2 * nw) {
+                const int g2 = g + nw;
+                const int c0 = g * KMCB200_DOT_GROUP + lane, d0 = g2 * KMCB200_DOT_GROUP + lane;
+                const bool two = g2 < nloc;
+                double v0 = (c0 < local_chunks) ? __ldcg(part + c0) : 0.0;
+                double v1 = (c0 + 32 < local_chunks) ? __ldcg(part + c0 + 32) : 0.0;
+                double u0 = (two && d0 < local_chunks) ? __ldcg(part + d0) : 0.0;
+                double u1 = (two && d0 + 32 < local_chunks) ? __ldcg(part + d0 + 32) : 0.0;
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) {
+                    const double a0 = __shfl_xor_sync(KMC_FULL_MASK, v0, off), a1 = __shfl_xor_sync(KMC_FULL_MASK, v1, off);
+                    const double b0 = __shfl_xor_sync(KMC_FULL_MASK, u0, off), b1 = __shfl_xor_sync(KMC_FULL_MASK, u1, off);
+                    v0 = v0 + a0; v1 = v1 + a1; u0 = u0 + b0; u1 = u1 + b1;
+                }
+                double tot = v0 + v1, tot2 = u0 + u1;
+#pragma unroll
+                for (int q = 0; q < 6; ++q) { tot = tot + 0.0; tot2 = tot2 + 0.0; }  // the six empty warps of chunk_reduce_256
+                // lanes 0..size-1 deliver: lane == rank keeps the plain copy, every other lane serves one peer
+                if (lane < cm.size) {
+                    if (lane == cm.rank) {
+                        table[(size_t)(slot0 + sidx) * tstride + first + g] = tot;
+                        if (two) table[(size_t)(slot0 + sidx) * tstride + first + g2] = tot2;
+                    } else {
+                        uint4 *cells = cm.peer_ll[lane] + cell0 + (size_t)sidx * nglob + first;
+                        kmc_ll_store(cells + g, tot, s32);
+                        if (two) kmc_ll_store(cells + g2, tot2, s32);
+                    }
+                }
+            }
+        }
+    } else {
+        for (int sidx = 0; sidx < nslots; ++sidx) {
+            const double *part = cm.partials + (size_t)(slot0 + sidx) * cm.nchunks_global + cm.chunk_start;
+            for (int i = threadIdx.x; i < nloc; i += blockDim.x) {
+                const double v = __ldcg(part + i);
+                for (int q = 0; q < cm.size; ++q)
+                    if (q != cm.rank) kmc_ll_store(cm.peer_ll[q] + cell0 + (size_t)sidx * nglob + first + i, v, s32);
+            }
+        }
+    }
+    // collect the other ranks' cells
+    unsigned long long deadline = 0;
+    for (int sidx = 0; sidx < nslots; ++sidx) {
+        const uint4 *cells = cm.ll + cell0 + (size_t)sidx * nglob;
+        double *trow = table + (size_t)(slot0 + sidx) * tstride;
+        for (int idx = threadIdx.x; idx < nglob; idx += blockDim.x) {
+            if (idx >= first && idx < first + nloc) continue;
+            double v = 0.0;
+            unsigned spins = 0;
+            while (!kmc_ll_try_load(cells + idx, s32, &v)) {
+                if ((++spins & 1023u) == 0) {
+                    const unsigned long long now = kmc_globaltimer_ns();
+                    if (deadline == 0) deadline = now + cm.timeout_ns;
+                    else if (now > deadline || (cm.err && *(volatile int *)cm.err)) {
+                        if (cm.err) *(volatile int *)cm.err = 1;
+                        break;
+                    }
+                }
+            }
+            trow[idx] = v;
+        }
+    }
+    __syncthreads();
+    for (int sidx = 0; sidx < nslots; ++sidx) {
+        const double *trow = table + (size_t)(slot0 + sidx) * tstride;
+        out[sidx] = grp ? final_reduce_wide(trow, nglob, red) : kmc_final_reduce(trow, nglob, red);
+    }
+}
 __device__ __forceinline__ void finish_dots(const CommDev &cm, int slot0, int nslots, int local_chunks,
                                             unsigned long long seq, double *red, double *out) {
+    if (cm.ll_mode) {
+        finish_dots_ll(cm, slot0, nslots, local_chunks, seq, red, out);
+        return;
+    }
     if (cm.group_chunks == 0) {
         exchange_partials(cm, slot0, nslots, local_chunks, seq);
         for (int sidx = 0; sidx < nslots; ++sidx)
@@ -161,6 +252,19 @@ __device__ __forceinline__ void finish_dots(const CommDev &cm, int slot0, int ns
     for (int sidx = 0; sidx < nslots; ++sidx)
         out[sidx] = final_reduce_wide(cm.gtotals + (size_t)(slot0 + sidx) * cm.ngroups_global, cm.ngroups_global, red);
 }
+// z halo (CommDev::ll_mode): the kernel that computes z[i] stores it into the z_full of every peer whose matrix block
+// references global row g.  Returns whether a remote store was issued (the thread fences those before the kernel ends).
+__device__ __forceinline__ bool push_z_halo(const CommDev &cm, int i, int g, double zi) {
+    unsigned m = cm.send_mask[i];
+    const bool any = m != 0;
+    while (m) {
+        const int q = __ffs(m) - 1;
+        m &= m - 1;
+        cm.peer_z_full[q][g] = zi;
+    }
+    return any;
+}
+
 // ---- completion of a dot product: exchange with the peers, reduce in the fixed order, update the PCG state.  Runs either
 // in the last CTA of the producing kernel (small problems: saves a launch) or in the 1-CTA dot_finalize_kernel (large
 // problems: the producing kernel's CTAs then need no fence / atomic at all).
@@ -205,6 +309,8 @@ __device__ __forceinline__ void finish_init(const CommDev &cm, int local_chunks,
 __global__ void __launch_bounds__(FIN_WIDE) dot_finalize_kernel(CommDev cm, int kind, int local_chunks, unsigned long long seq,
                                                          CgState *__restrict__ st) {
     __shared__ double red[8];
+    kmc_pdl_trigger();
+    kmc_pdl_wait();
     if (kind != 2 && st->done) return;
     if (kind == 0) finish_pap(cm, local_chunks, seq, st, red);
     else if (kind == 1) finish_rz(cm, local_chunks, seq, st, red);
@@ -221,6 +327,8 @@ __global__ void __launch_bounds__(CH) spmv_kernel(int rows, const int *__restric
                                                  const int *__restrict__ col, const double *__restrict__ val,
                                                  const double *__restrict__ xg, double *__restrict__ y, CommDev cm,
                                                  unsigned long long dot_seq, CgState *__restrict__ st) {
+    kmc_pdl_trigger();
+    kmc_pdl_wait();
     if (DOT && st->done) return;
     __shared__ double prod[DOT ? CH : 1];
     __shared__ double red[8];
@@ -362,6 +470,8 @@ __global__ void __launch_bounds__(CH) cg_init_kernel(int rows, int nchunks, doub
                                                     unsigned long long dot_seq, CgState *__restrict__ st) {
     __shared__ double red[8];
     __shared__ int flag;
+    const bool zh = cm.ll_mode != 0;
+    bool remote = false;
     for (int c = blockIdx.x; c < nchunks; c += gridDim.x) {
         int i = c * CH + threadIdx.x;
         double vbb = 0.0, vrz = 0.0;
@@ -371,6 +481,7 @@ __global__ void __launch_bounds__(CH) cg_init_kernel(int rows, int nchunks, doub
             double zi = ri * __ldcs(dinv + i);
             __stcs(r + i, ri);
             __stcs(z + i, zi);
+            if (zh) remote |= push_z_halo(cm, i, cm.row_start + i, zi);
             vbb = b * b;
             vrz = ri * zi;
         }
@@ -381,7 +492,9 @@ __global__ void __launch_bounds__(CH) cg_init_kernel(int rows, int nchunks, doub
             publish_partial(cm, 3, c, crz);
         }
     }
+    if (remote) __threadfence_system();  // z halo stores performed at the peers before this rank's dot cells can leave
     if (FUSE) {
+        if (zh) __syncthreads();
         if (last_cta(&st->cnt[1], &flag, false)) {
             finish_init(cm, nchunks, dot_seq, st, red);
             if (threadIdx.x == 0) st->cnt[1] = 0;
@@ -399,10 +512,15 @@ __global__ void __launch_bounds__(CH) cg_pupdate_kernel(int rows, int nchunks, c
                                                        const double *__restrict__ p_old, double *__restrict__ p_new,
                                                        CommDev cm, int buf, unsigned long long halo_seq,
                                                        CgState *__restrict__ st) {
+    kmc_pdl_trigger();
+    kmc_pdl_wait();
     if (MODE == 1 && st->done) return;
     __shared__ int flag;
     const bool first = (MODE == 0) || (st->k == 1);
     const double beta = first ? 0.0 : st->rz / st->rz_old;
+    // ll_mode: p is not exchanged inside the loop -- the halo entries of p are formed here from the z halo the peers
+    // delivered (same operands, same operations as on the owner)
+    const bool zh = (MODE == 1) && cm.ll_mode != 0;
     int remote = 0;
     for (int c = blockIdx.x; c < nchunks; c += gridDim.x) {
         int i = c * CH + threadIdx.x;
@@ -417,7 +535,7 @@ __global__ void __launch_bounds__(CH) cg_pupdate_kernel(int rows, int nchunks, c
                 v = __ldcs(src + i) + t;
             }
             p_new[g] = v;
-            if (cm.size > 1) {
+            if (cm.size > 1 && !zh) {
                 unsigned m = cm.send_mask[i];
                 remote |= (m != 0);
                 while (m) {
@@ -428,7 +546,20 @@ __global__ void __launch_bounds__(CH) cg_pupdate_kernel(int rows, int nchunks, c
             }
         }
     }
-    if (cm.size > 1) {
+    if (zh) {
+        for (int h = blockIdx.x * CH + threadIdx.x; h < cm.nhalo; h += gridDim.x * CH) {
+            const int g = __ldg(cm.halo_rows + h);
+            double v;
+            if (first) {
+                v = __ldcs(cm.z_full + g);
+            } else {
+                double t = beta * __ldcs(p_old + g);
+                v = __ldcs(cm.z_full + g) + t;
+            }
+            p_new[g] = v;
+        }
+    }
+    if (cm.size > 1 && !zh) {
         remote = __syncthreads_or(remote);
         if (last_cta(&st->cnt[4], &flag, remote != 0)) {
             if (threadIdx.x == 0) {
@@ -450,11 +581,15 @@ __global__ void __launch_bounds__(CH) cg_update_kernel(int rows, int nchunks, co
                                                       double *__restrict__ x, double *__restrict__ r,
                                                       double *__restrict__ z, CommDev cm,
                                                       unsigned long long dot_seq, CgState *__restrict__ st) {
+    kmc_pdl_trigger();
+    kmc_pdl_wait();
     if (st->done) return;
     __shared__ double red[8];
     __shared__ int flag;
     const double a = st->rz / st->pAp;
     const double na = -a;
+    const bool zh = cm.ll_mode != 0;
+    bool remote = false;
     for (int c = blockIdx.x; c < nchunks; c += gridDim.x) {
         int i = c * CH + threadIdx.x;
         double v = 0.0;
@@ -466,12 +601,15 @@ __global__ void __launch_bounds__(CH) cg_update_kernel(int rows, int nchunks, co
             __stcs(x + i, xi);
             __stcs(r + i, ri);
             __stcs(z + i, zi);
+            if (zh) remote |= push_z_halo(cm, i, cm.row_start + i, zi);
             v = ri * zi;
         }
         double cv = kmc_chunk_reduce_256(v, red);
         if (threadIdx.x == 0) publish_partial(cm, 1, c, cv);
     }
+    if (remote) __threadfence_system();  // z halo stores performed at the peers before this rank's dot cells can leave
     if (FUSE) {
+        if (zh) __syncthreads();
         if (last_cta(&st->cnt[2], &flag, false)) {
             finish_rz(cm, nchunks, dot_seq, st, red);
             if (threadIdx.x == 0) st->cnt[2] = 0;
@@ -919,7 +1057,7 @@ int ensure_cg_workspace(kmcb200_ctx *ctx, long long nchunks) {
 // fuse_final: the SpMV's last CTA completes the dot product itself (small problems); otherwise the caller launches
 // dot_finalize_kernel afterwards.
 static int spmv_launch(kmcb200_ctx *ctx, kmcb200_kmat *K, const double *xg, double *y, bool with_dot, int fuse_final,
-                       unsigned long long dot_seq) {
+                       unsigned long long dot_seq, bool pdl = false) {
     constexpr int L = KMCB200_SPMV_LANES;
     const CommDev &cm = K->comm->dev;
     unsigned blocks = (unsigned)((K->rows + CH - 1) / CH);
@@ -941,9 +1079,9 @@ static int spmv_launch(kmcb200_ctx *ctx, kmcb200_kmat *K, const double *xg, doub
                                                                           K->u_col, xg, y, cm, ctx->cg_state);
     } else {
         static const int depth = getenv("KMCB200_SPMV_DEPTH") ? atoi(getenv("KMCB200_SPMV_DEPTH")) : 4;
-#define KMC_SPMV_GO(DOTV, D, F)                                                                                  \
-    spmv_kernel<L, DOTV, D, F><<<blocks, CH, 0, ctx->stream>>>(K->rows, K->row_ptr, K->col, K->val, xg, y, cm, dot_seq, \
-                                                              ctx->cg_state)
+#define KMC_SPMV_GO(DOTV, D, F)                                                                                      \
+    KMC_CUDA(kmc_launch_pdl(spmv_kernel<L, DOTV, D, F>, blocks, CH, 0, ctx->stream, pdl, K->rows, (const int *)K->row_ptr, \
+                            (const int *)K->col, (const double *)K->val, xg, y, cm, dot_seq, ctx->cg_state))
         if (with_dot && fuse_final) {
             if (depth <= 4) KMC_SPMV_GO(true, 4, true); else KMC_SPMV_GO(true, 7, true);
         } else if (with_dot) {
@@ -1178,6 +1316,11 @@ int kmc_pcg_run(kmcb200_ctx *ctx, kmcb200_kmat *K, const TunnelDev *tun, double 
         }
     }
     int batch = 4;
+    // Programmatic dependent launch for the kernels of the iteration (KMCB200_PDL=0 switches it off): each kernel's launch
+    // and CTA ramp-up overlap the tail of its predecessor; the kernels wait (griddepcontrol.wait) before their first access.
+    static const bool pdl_env = !(getenv("KMCB200_PDL") && atoi(getenv("KMCB200_PDL")) == 0);
+    const bool pdl = pdl_env && !tun;
+    const unsigned fin_threads = C->dev.group_chunks ? FIN_WIDE : CH;
     // KMCB200_PCG_PROFILE=1: CUDA events around every kernel of the iteration (diagnostics only; serialises nothing
     // by itself, the events sit on the same stream)
     static const bool profile = getenv("KMCB200_PCG_PROFILE") != nullptr;
@@ -1200,13 +1343,13 @@ int kmc_pcg_run(kmcb200_ctx *ctx, kmcb200_kmat *K, const TunnelDev *tun, double 
             cudaEvent_t *pe = pev + 4 * b;
             if (rec) cudaEventRecord(pe[0], ctx->stream);
             kmc_count_launch();
-            cg_pupdate_kernel<1><<<eb, CH, 0, ctx->stream>>>(rows, (int)nchunks, K->z, C->dev.p_full[nb ^ 1], C->dev.p_full[nb],
-                                                            C->dev, nb, hs2, st);
+            KMC_CUDA(kmc_launch_pdl(cg_pupdate_kernel<1>, eb, CH, 0, ctx->stream, pdl, rows, (int)nchunks, K->z,
+                                    C->dev.p_full[nb ^ 1], C->dev.p_full[nb], C->dev, nb, hs2, st));
             if (rec) cudaEventRecord(pe[1], ctx->stream);
             if (!tun) {
                 const unsigned long long ds = ++C->dot_seq;
-                KMC_TRY(spmv_launch(ctx, K, C->dev.p_full[nb], K->Ap, true, fuse, ds));
-                if (!fuse) { kmc_count_launch(); dot_finalize_kernel<<<1, C->dev.group_chunks ? FIN_WIDE : CH, 0, ctx->stream>>>(C->dev, 0, (int)nchunks, ds, st); }
+                KMC_TRY(spmv_launch(ctx, K, C->dev.p_full[nb], K->Ap, true, fuse, ds, pdl));
+                if (!fuse) { kmc_count_launch(); KMC_CUDA(kmc_launch_pdl(dot_finalize_kernel, 1u, fin_threads, 0, ctx->stream, pdl, C->dev, 0, (int)nchunks, ds, st)); }
             } else {  // neighbour part, tunnel part, then p.Ap over the sum
                 const unsigned long long ds = ++C->dot_seq;
                 KMC_TRY(spmv_launch(ctx, K, C->dev.p_full[nb], K->Ap, false, 0, 0));
@@ -1221,12 +1364,12 @@ int kmc_pcg_run(kmcb200_ctx *ctx, kmcb200_kmat *K, const TunnelDev *tun, double 
             {
                 const unsigned long long ds = ++C->dot_seq;
                 if (fuse)
-                    cg_update_kernel<true><<<eb, CH, 0, ctx->stream>>>(rows, (int)nchunks, C->dev.p_full[nb], K->Ap, diag_inv_local,
-                                                                      x_local, r_local, K->z, C->dev, ds, st);
+                    KMC_CUDA(kmc_launch_pdl(cg_update_kernel<true>, eb, CH, 0, ctx->stream, pdl, rows, (int)nchunks, C->dev.p_full[nb],
+                                            K->Ap, diag_inv_local, x_local, r_local, K->z, C->dev, ds, st));
                 else
-                    cg_update_kernel<false><<<eb, CH, 0, ctx->stream>>>(rows, (int)nchunks, C->dev.p_full[nb], K->Ap, diag_inv_local,
-                                                                       x_local, r_local, K->z, C->dev, ds, st);
-                if (!fuse) { kmc_count_launch(); dot_finalize_kernel<<<1, C->dev.group_chunks ? FIN_WIDE : CH, 0, ctx->stream>>>(C->dev, 1, (int)nchunks, ds, st); }
+                    KMC_CUDA(kmc_launch_pdl(cg_update_kernel<false>, eb, CH, 0, ctx->stream, pdl, rows, (int)nchunks, C->dev.p_full[nb],
+                                            K->Ap, diag_inv_local, x_local, r_local, K->z, C->dev, ds, st));
+                if (!fuse) { kmc_count_launch(); KMC_CUDA(kmc_launch_pdl(dot_finalize_kernel, 1u, fin_threads, 0, ctx->stream, pdl, C->dev, 1, (int)nchunks, ds, st)); }
             }
             if (rec) cudaEventRecord(pe[3], ctx->stream);
             launched_iters++;

@@ -246,6 +246,8 @@ def pcg_fixed_iterations(kmc, ctx, s, rank, world, dist, iters=60, solves=3):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         if k > 0:
             times.append(float(t.item()) / max(it, 1))
+    import hashlib
+    x_sha1 = hashlib.sha1(xsol.cpu().numpy().tobytes()).hexdigest()[:16]   # this rank's slice of the iterate (A/B runs must agree bit for bit)
     nnz_local = K.nnz
     tot = torch.tensor([float(nnz_local)], device=c.device, dtype=torch.float64)
     if world > 1:
@@ -255,7 +257,7 @@ def pcg_fixed_iterations(kmc, ctx, s, rank, world, dist, iters=60, solves=3):
     out = {"N": int(s.N), "rows": int(n), "nnz": int(nnz), "gpus": world, "iterations_per_solve": iters,
            "ms_per_pcg_iteration": ms_it,
            "GBs_per_gpu": (12.0 * nnz + 108.0 * n) / world / (ms_it * 1e-3) / 1e9,
-           "partition_rows": [int(v) for v in counts]}
+           "partition_rows": [int(v) for v in counts], "x_sha1_rank0": x_sha1}
     K.close(); comm.close()
     return out
 
