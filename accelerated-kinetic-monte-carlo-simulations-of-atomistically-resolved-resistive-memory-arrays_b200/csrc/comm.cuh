@@ -2,12 +2,17 @@
 //
 // Replaces the reference's GPU-aware MPI traffic inside the PCG: the pack -> MPI_Isend/Irecv -> unpack halo exchange of
 // dspmv::gpu_packing_cam (dist_iterative/dist_spmv_gpu_packing.cpp:106-228) and the MPI_Allreduce after every hipblasDdot
-// (dist_iterative/dist_conjugate_gradient.cpp:188,213,241,265).  Here the kernel that PRODUCES a value also delivers it:
+// (dist_iterative/dist_conjugate_gradient.cpp:188,213,241,265).  Here the kernel that PRODUCES a value also delivers it.
+// Inside the PCG loop (CommDev::ll_mode, the default; see the comment at that field):
+//   * the kernels that compute z store the z entries a peer's matrix block references into that peer's z_full; every
+//     rank forms the halo entries of p itself, so p is not exchanged;
+//   * dot contributions (group totals / chunk partials) travel as self-validating 16-byte cells; every rank then reduces
+//     ALL contributions in the fixed order of the summation spec, so every rank holds the bit-identical scalar without a
+//     collective call or a host round trip.
+// One-off sharded SpMVs (kmcb200_spmv, A x0 of a solve) and KMCB200_COMM_LL=0 use the flag protocol:
 //   * the p-update kernel stores each new p entry into its own p vector and, for rows a peer's matrix block
 //     references, directly into that peer's p vector (remote NVLink stores), then raises a flag;
-//   * every dot-producing kernel stores its 256-row chunk partials into all peers' partial arrays; the last CTA of
-//     each rank waits for the peers' flags and reduces ALL partials in the fixed order of the summation spec, so every
-//     rank holds the bit-identical scalar without a collective call or a host round trip.
+//   * the dot-completing CTA pushes its contributions to all peers' arrays, fences, raises a flag and waits for theirs.
 // With size == 1 the same kernels run with empty peer loops (this is the single-GPU path).
 #pragma once
 #include "common.cuh"

@@ -3,8 +3,10 @@
 // Reference: dist_iterative/dist_conjugate_gradient.cpp:149-276 (update order kept exactly),
 // dist_iterative/dist_spmv_gpu_packing.cpp:106-228 (SpMV + halo), dist_iterative/utils_cg.cu:323-371 (elementwise).
 // The reference runs per iteration: one rocsparse_spmv per neighbour block with pack/Isend/Irecv/unpack, 2 hipblasDdot
-// (each a blocking host round trip + MPI_Allreduce), 3 daxpy, 1 dscal, 1 elementwise.  Here: 3 kernels per iteration,
-// all scalars stay on the device, halo entries and dot partials are delivered to the peers by the producing kernels.
+// (each a blocking host round trip + MPI_Allreduce), 3 daxpy, 1 dscal, 1 elementwise.  Here: 3 kernels per iteration
+// (5 above 1024 chunks, where a 1-CTA kernel completes each dot), chained by programmatic dependent launch; all scalars
+// stay on the device; on several GPUs the z halo and the dot contributions are delivered to the peers by the kernels
+// that produce them, two exchanges per iteration, no fence or flag on the critical path (comm.cuh).
 #include <stdlib.h>
 #include <string.h>
 
@@ -618,7 +620,7 @@ __global__ void __launch_bounds__(CH) cg_update_kernel(int rows, int nchunks, co
 }
 
 // ================================ the whole PCG loop as ONE persistent cooperative kernel =============================
-//   grid = as many 256-thread CTAs as are co-resident; a CTA walks the dot chunks c = blockIdx.x,
+// (opt-in.)  grid = as many 256-thread CTAs as are co-resident; a CTA walks the dot chunks c = blockIdx.x,
 // blockIdx.x + gridDim.x, ... in every phase.  Per iteration: p update (+ halo push) | grid barrier (+ halo flags) |
 // SpMV + p.Ap chunk partials | grid barrier (+ dot flags) | x, r, z update + r.z chunk partials | grid barrier (+ dot
 // flags).  The arithmetic, its order and the summation spec are those of the kernels above (same device functions), so
@@ -1252,7 +1254,7 @@ int kmc_pcg_run(kmcb200_ctx *ctx, kmcb200_kmat *K, const TunnelDev *tun, double 
     KMC_CUDA(cudaGetLastError());
     // ---- the iterations: the multi-kernel loop below (default), or ONE persistent cooperative kernel
     // (KMCB200_PCG_PERSISTENT=1; not for the tunnel operator).  Measured on one B200 at 2.3 M rows: 254 vs 226 us per
-    // iteration -- see DESIGN.md 10.1 for why the persistent form loses there.
+    // iteration -- see DESIGN.md 6 / profiles/r2_pcg_multigpu.md: the persistent form is slower at every size measured.
     const bool want_persist = getenv("KMCB200_PCG_PERSISTENT") != nullptr && atoi(getenv("KMCB200_PCG_PERSISTENT")) != 0 &&
                               getenv("KMCB200_PCG_PROFILE") == nullptr;  // (read per call: the tests switch it)
     const bool persistent = !tun && want_persist;
