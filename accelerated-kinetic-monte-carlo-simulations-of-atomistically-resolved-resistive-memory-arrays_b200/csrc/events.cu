@@ -53,6 +53,8 @@ struct kmcb200_events {
     // 1..255 and advances with every build, so the flags of older lists expire without a pass over the array.
     unsigned char *revpos = nullptr, *nzflag = nullptr;
     int gen = 0;
+    unsigned char *row_active = nullptr;  // N bytes: the site could start an event at the last rate build (build_rates_kernel)
+    bool list_built = false;              // false until the first build has written every row of prob / type
     unsigned *mt = nullptr;  // 624 words + pos
     int *log = nullptr;
     double *log_psum = nullptr;
@@ -279,6 +281,11 @@ __device__ __forceinline__ double event_rate(int i, int j, int el_i, int c_i, do
 
 // One CTA per chunk of 256 rows; each of its 8 warps walks 32 rows, lanes cover the nn (<= 64) slots of a row.
 // Writes event_prob / event_type (coalesced), the row sums and the chunk sum.
+// Incremental across supersteps: a row whose site can start no event (an ordinary lattice atom: ~95 % of the
+// sites) holds 52 zero rates and NULL types.  Such a row is written only if it COULD act at the previous build
+// (row_active, one byte per site); rows that were and are inactive still hold the zeros of an earlier build -- the event
+// loop only ever clears slots -- and are skipped, which takes ~1.1 GB of stores per superstep down to the active rows.
+// full != 0 (first build of a list): every row is written.
 __global__ void __launch_bounds__(256) build_rates_kernel(int N, int nn, const int *__restrict__ neigh,
                                                          const int *__restrict__ layer, double kT, double freq,
                                                          double sigma, double k, const double *__restrict__ x,
@@ -290,16 +297,28 @@ __global__ void __launch_bounds__(256) build_rates_kernel(int N, int nn, const i
                                                          double *__restrict__ rowsum, double *__restrict__ chunksum,
                                                          double *__restrict__ rowincl,
                                                          const unsigned char *__restrict__ revpos,
-                                                         unsigned char *__restrict__ nzflag, int gen) {
+                                                         unsigned char *__restrict__ nzflag, int gen,
+                                                         unsigned char *__restrict__ row_active, int full) {
     __shared__ double rs[256];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int row0 = blockIdx.x * 256 + w * 32;
     double my_rowsum = 0.0;  // lane q ends up holding the sum of row row0 + q
-    for (int q = 0; q < 32; ++q) {
+    int my_el = -1;
+    bool my_act = false, my_was = false;
+    if (row0 + lane < N) {
+        my_el = element[row0 + lane];
+        my_act = (my_el == KMCB200_DEFECT || my_el == KMCB200_OXYGEN_DEFECT || my_el == KMCB200_VACANCY);
+        my_was = full || row_active[row0 + lane] != 0;
+        row_active[row0 + lane] = my_act ? 1 : 0;
+    }
+    unsigned todo = __ballot_sync(KMC_FULL_MASK, my_act || my_was);
+    while (todo) {
+        const int q = __ffs(todo) - 1;
+        todo &= todo - 1;
         int i = row0 + q;
         double s = 0.0;
-        if (i < N) {
-            int el_i = element[i];
+        {
+            int el_i = __shfl_sync(KMC_FULL_MASK, my_el, q);
             bool can_act = (el_i == KMCB200_DEFECT || el_i == KMCB200_OXYGEN_DEFECT || el_i == KMCB200_VACANCY);
             double P0 = 0.0, P1 = 0.0;
             int e0 = KMCB200_NULL_EVENT, e1 = KMCB200_NULL_EVENT;
@@ -1292,6 +1311,7 @@ extern "C" int kmcb200_events_create(kmcb200_ctx *ctx, int N, int nn, const int 
     auto A = [&](void **p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
     A((void **)&ev->prob, (size_t)total * sizeof(double));
     A((void **)&ev->type, (size_t)total);
+    A((void **)&ev->row_active, (size_t)N);
     A((void **)&ev->rowsum, (size_t)ev->nchunk * 256 * 2 * sizeof(double));  // rowsum | rowincl, padded to whole chunks (tail stays 0)
     A((void **)&ev->chunksum, (size_t)ev->nsuper * 256 * sizeof(double));  // padded to whole supers (tail stays 0)
     A((void **)&ev->supersum, (size_t)MAX_SUPER * sizeof(double));
@@ -1365,7 +1385,7 @@ extern "C" int kmcb200_events_create(kmcb200_ctx *ctx, int N, int nn, const int 
 extern "C" int kmcb200_events_destroy(kmcb200_events *ev) {
     if (!ev) return 0;
     if (ev->ctx) cudaStreamSynchronize(ev->ctx->stream);
-    cudaFree(ev->prob); cudaFree(ev->type); cudaFree(ev->rowsum); cudaFree(ev->chunksum); cudaFree(ev->supersum);
+    cudaFree(ev->prob); cudaFree(ev->type); cudaFree(ev->row_active); cudaFree(ev->rowsum); cudaFree(ev->chunksum); cudaFree(ev->supersum);
     cudaFree(ev->chunkincl);
     cudaFree(ev->rev); cudaFree(ev->revpos); cudaFree(ev->nzflag); cudaFree(ev->mt); cudaFree(ev->log); cudaFree(ev->log_psum);
     cudaFree(ev->result);
@@ -1449,8 +1469,10 @@ extern "C" int kmcb200_build_event_list(kmcb200_ctx *ctx, kmcb200_events *ev, in
                                                                      z, site_potential_charge, site_element,
                                                                      site_charge, ev->energies, ev->prob, ev->type,
                                                                      ev->rowsum, ev->chunksum, ev->rowincl, ev->revpos,
-                                                                     ev->nzflag, ev->gen);
+                                                                     ev->nzflag, ev->gen, ev->row_active,
+                                                                     ev->list_built ? 0 : 1);
     KMC_CUDA(cudaGetLastError());
+    ev->list_built = true;
     kmc_count_launch();
     super_sums_kernel<<<(unsigned)ev->nsuper, 32, 0, ctx->stream>>>(ev->chunksum, ev->nchunk, ev->supersum,
                                                                      ev->chunkincl);

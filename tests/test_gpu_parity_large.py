@@ -108,13 +108,17 @@ def test_persistent_pcg_kernel_vs_oracle(kmc, ctx, orc):
             os.environ["KMCB200_PCG_PERSISTENT"] = old
 
 
-@pytest.mark.parametrize("persistent", ["0", "1"])
-def test_sharded_solve_two_processes_vs_oracle(kmc, tmp_path, persistent):
+@pytest.mark.parametrize("mode", ["cells", "flags", "persistent"])
+def test_sharded_solve_two_processes_vs_oracle(kmc, tmp_path, mode):
     """Row-sharded K solve + sharded Coulomb sum on 2 ranks against the ORACLE, on the kernel paths
     bench.py runs at N > 1: 4x4 stand-in = 2 282 dot chunks -> FUSE=false kernels + dot_finalize with the two-level
     (group-total) exchange, halo pushes, NVLink all-gather of the potentials.  Driven through the C ABI only (file
     rendezvous + CUDA IPC, no NCCL), so both ranks can share GPU 0 on a one-GPU box: the test never skips.
-    persistent = "1": the same with the opt-in one-kernel PCG loop (grid barriers + peer flags inside the kernel)."""
+    mode "cells" (the default protocol): z halo + locally formed p halo, dot contributions as self-validating 16-byte
+    cells, no fence / flag in the loop; "flags" (KMCB200_COMM_LL=0): p halo pushes + fence + flag exchanges;
+    "persistent": the opt-in one-kernel PCG loop (grid barriers + peer flags inside the kernel)."""
+    persistent = "1" if mode == "persistent" else "0"
+    ll = "0" if mode == "flags" else "1"
     import json
     import subprocess
     import sys
@@ -123,7 +127,8 @@ def test_sharded_solve_two_processes_vs_oracle(kmc, tmp_path, persistent):
     worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "mgpu_cabi_worker.py")
     procs = [subprocess.Popen([sys.executable, worker, str(r), "2", str(tmp_path / "rdv"), str(r if ngpu >= 2 else 0), "4"],
                               stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
-                              env=dict(os.environ, KMCB200_COMM_TIMEOUT_MS="120000", KMCB200_PCG_PERSISTENT=persistent))
+                              env=dict(os.environ, KMCB200_COMM_TIMEOUT_MS="120000", KMCB200_PCG_PERSISTENT=persistent,
+                                       KMCB200_COMM_LL=ll))
              for r in range(2)]
     outs = [p.communicate(timeout=1500) for p in procs]
     reps = []
