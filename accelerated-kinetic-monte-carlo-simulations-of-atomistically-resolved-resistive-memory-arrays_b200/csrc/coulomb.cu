@@ -212,6 +212,13 @@ constexpr int TILE = 128;  // sources per shared-memory tile
 
 // potential_solver_gpu.cu:1541-1562: V_i = sum_j v_solve(1e-10*|r_ij|, q_j), ascending j, overwrite.
 // One CTA = up to CT targets of one cell; sources = that cell's neighbourhood list, tiled through shared memory.
+// Two phases per tile, because only ~15 % of the tested pairs are inside the cutoff and a thread-per-target loop that
+// evaluates erfc / div under the test runs that path with ~5 of 32 lanes active:
+//   1. every thread tests its target against the tile's sources on the SQUARED distance (d2 <= d2max is exactly
+//      sqrt(d2) < cutoff: d2max is the largest double whose correctly rounded square root is below the cutoff, found on
+//      the host) and queues the tile positions of its hits (one byte each, shared memory, [slot][thread]);
+//   2. the threads evaluate their queued hits in lock-step, in queue (= ascending source) order, so a target's sum keeps
+//      the reference's order and bits while the expensive path runs with most lanes active.
 __global__ void __launch_bounds__(CT) coulomb_cell_kernel(const double *__restrict__ x, const double *__restrict__ y,
                                                          const double *__restrict__ z, const Source *__restrict__ src,
                                                          const int *__restrict__ blk_cell,
@@ -220,10 +227,11 @@ __global__ void __launch_bounds__(CT) coulomb_cell_kernel(const double *__restri
                                                          const int *__restrict__ titems,
                                                          const int *__restrict__ list_start,
                                                          const int *__restrict__ lists, double sigma, double k,
-                                                         double cutoff, int row_start, int row_count,
+                                                         double d2max, int row_start, int row_count,
                                                          double *__restrict__ pot,
                                                          unsigned long long *__restrict__ pair_counter) {
     __shared__ Source tile[TILE];
+    __shared__ unsigned char hitq[TILE][CT];
     const int c = blk_cell[blockIdx.x];
     const int tpos = cell_tstart[c] + (blockIdx.x - blk_start[c]) * CT + threadIdx.x;
     const bool in_cell = tpos < cell_tstart[c + 1];
@@ -239,17 +247,24 @@ __global__ void __launch_bounds__(CT) coulomb_cell_kernel(const double *__restri
         __syncthreads();
         if (threadIdx.x < nt) tile[threadIdx.x] = src[lists[base + threadIdx.x]];
         __syncthreads();
+        int nq = 0;
         if (active) {
+#pragma unroll 4
             for (int t = 0; t < nt; ++t) {
-                Source s = tile[t];
-                double d = kmc_dist_nopbc(xi, yi, zi, s.x, s.y, s.z);
-                if (d < cutoff && s.idx != i) {
-                    double dist = 1e-10 * d;
-                    local += kmc_v_solve(dist, s.charge, sigma, k);
-                    ++hits;
-                }
+                const double dx = tile[t].x - xi, dy = tile[t].y - yi, dz = tile[t].z - zi;
+                const double d2 = dx * dx + dy * dy + dz * dz;  // the argument of kmc_dist_nopbc's sqrt, same roundings
+                if (d2 <= d2max && tile[t].idx != i) hitq[nq++][threadIdx.x] = (unsigned char)t;
             }
         }
+        const int nq_warp = __reduce_max_sync(KMC_FULL_MASK, nq);
+        for (int q = 0; q < nq_warp; ++q) {
+            if (q < nq) {
+                const Source s = tile[hitq[q][threadIdx.x]];
+                const double dist = 1e-10 * kmc_dist_nopbc(xi, yi, zi, s.x, s.y, s.z);
+                local += kmc_v_solve(dist, s.charge, sigma, k);
+            }
+        }
+        hits += nq;
     }
     if (active) pot[i] = local;
     if (pair_counter) {
@@ -437,9 +452,13 @@ extern "C" int kmcb200_poisson_gridless(kmcb200_ctx *ctx, int N, const double *x
     // 3. the pair sum
     unsigned long long *pairs = csum;  // csum[0] (tests) and csum[3] (in range, via pairs_in) were zeroed above
     if (P.nblocks > 0) {
+        // largest double whose (correctly rounded) square root is still below the cutoff: d2 <= d2max <=> sqrt(d2) < cutoff
+        double d2max = cutoff_radius * cutoff_radius;
+        while (sqrt(d2max) >= cutoff_radius) d2max = nextafter(d2max, 0.0);
+        while (sqrt(nextafter(d2max, INFINITY)) < cutoff_radius) d2max = nextafter(d2max, INFINITY);
         kmc_count_launch();
         coulomb_cell_kernel<<<P.nblocks, CT, 0, ctx->stream>>>(x, y, z, src, P.blk_cell, P.blk_start, P.cell_tstart,
-                                                              P.titems, P.list_start, lists, sigma, k, cutoff_radius,
+                                                              P.titems, P.list_start, lists, sigma, k, d2max,
                                                               row_start, row_count, site_potential_charge, pairs);
         KMC_CUDA(cudaGetLastError());
     }
