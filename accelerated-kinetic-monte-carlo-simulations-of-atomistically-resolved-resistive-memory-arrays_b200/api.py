@@ -123,6 +123,7 @@ SIGNATURES = {
     "kmcb200_comm_info": (_i, [_vp, _pi, _pi, C.POINTER(C.c_uint), _pll]),
     "kmcb200_poisson_gridless": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _d, _d, _d, _i, _i, _vp]),
     "kmcb200_poisson_stats": (_i, [_vp, _pll, _pll, _pll]),
+    "kmcb200_cutoff_d2max": (C.c_double, [C.c_double]),
     "kmcb200_sum_potential": (_i, [_vp, _i, _vp, _vp]),
     "kmcb200_events_create": (_i, [_vp, _i, _i, _vp, _pvp]),
     "kmcb200_events_destroy": (_i, [_vp]),

@@ -281,6 +281,15 @@ __global__ void sum_kernel(double *__restrict__ a, const double *__restrict__ b,
 
 }  // namespace
 
+// largest double whose (correctly rounded) square root is still below the cutoff: d2 <= d2max <=> sqrt(d2) < cutoff
+extern "C" double kmcb200_cutoff_d2max(double cutoff) {
+    if (!(cutoff > 0.0)) return -1.0;  // no pair is in range (d2 >= 0)
+    double d2max = cutoff * cutoff;
+    while (sqrt(d2max) >= cutoff) d2max = nextafter(d2max, 0.0);
+    while (sqrt(nextafter(d2max, INFINITY)) < cutoff) d2max = nextafter(d2max, INFINITY);
+    return d2max;
+}
+
 extern "C" int kmcb200_update_charge(kmcb200_ctx *ctx, const int *element, int *charge, const int *neigh, int N, int nn,
                                      const int *metals_host, int num_metals, int row_start, int row_count) {
     KMC_CHECK_ARG(ctx && element && charge && (neigh || row_count == 0), "null pointer");
@@ -452,10 +461,7 @@ extern "C" int kmcb200_poisson_gridless(kmcb200_ctx *ctx, int N, const double *x
     // 3. the pair sum
     unsigned long long *pairs = csum;  // csum[0] (tests) and csum[3] (in range, via pairs_in) were zeroed above
     if (P.nblocks > 0) {
-        // largest double whose (correctly rounded) square root is still below the cutoff: d2 <= d2max <=> sqrt(d2) < cutoff
-        double d2max = cutoff_radius * cutoff_radius;
-        while (sqrt(d2max) >= cutoff_radius) d2max = nextafter(d2max, 0.0);
-        while (sqrt(nextafter(d2max, INFINITY)) < cutoff_radius) d2max = nextafter(d2max, INFINITY);
+        const double d2max = kmcb200_cutoff_d2max(cutoff_radius);
         kmc_count_launch();
         coulomb_cell_kernel<<<P.nblocks, CT, 0, ctx->stream>>>(x, y, z, src, P.blk_cell, P.blk_start, P.cell_tstart,
                                                               P.titems, P.list_start, lists, sigma, k, d2max,

@@ -220,6 +220,10 @@ int kmcb200_poisson_gridless(kmcb200_ctx *ctx, int N, const double *x, const dou
 /* last poisson call (host sync): number of charged sources, (i,j) distance tests, pairs inside the cutoff (the ones
  * that evaluate erfc / division).  Any pointer may be NULL. */
 int kmcb200_poisson_stats(kmcb200_ctx *ctx, long long *num_charged, long long *pair_tests, long long *pairs_in_range);
+/* Host-only helper of the pair sum: the largest double d2max with sqrt(d2max) < cutoff (IEEE correctly rounded sqrt), so that
+ * the kernel's squared-distance test  d2 <= d2max  selects exactly the pairs of the reference's  sqrt(d2) < cutoff
+ * (src/potential_solver_gpu.cu:1549-1551).  Needs no device. */
+double kmcb200_cutoff_d2max(double cutoff);
 
 /* a9.  Replaces the kernel of sum_and_gather_potential (src/gpu_solvers.h:181,
  * src/potential_solver_gpu.cu:832-843,1130-1151): site_potential_charge += site_potential_boundary. */

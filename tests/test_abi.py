@@ -53,3 +53,27 @@ def test_product_does_not_touch_oracle():
                 assert "kmc_oracle" not in txt and "oracle.binding" not in txt and "from oracle" not in txt, f
     for hdr in os.listdir(os.path.join(ROOT, "include")):
         assert "kmc_oracle" not in open(os.path.join(ROOT, "include", hdr)).read()
+
+
+def test_cutoff_d2max_is_the_exact_squared_distance_threshold(kmc):
+    """kmcb200_cutoff_d2max (host-only): d2 <= d2max must select exactly the pairs with sqrt(d2) < cutoff, for the
+    reference's 20 A cutoff (src/potential_solver_gpu.cu:1549-1551) and for awkward cutoffs, checked on the doubles
+    around the boundary and on random squared distances (numpy's sqrt is IEEE correctly rounded, like the device's)."""
+    import numpy as np
+    lib = kmc.load_library()
+    rng = np.random.default_rng(7)
+    cutoffs = [20.0, 3.5, 1e-3, 12.5, np.nextafter(20.0, 0.0), np.nextafter(20.0, 100.0), float(np.sqrt(2.0)), 1e8] + \
+        list(rng.uniform(0.1, 50.0, 20))
+    for cutoff in cutoffs:
+        d2max = lib.kmcb200_cutoff_d2max(float(cutoff))
+        assert np.sqrt(d2max) < cutoff <= np.sqrt(np.nextafter(d2max, np.inf))
+        near = [d2max]
+        for _ in range(50):
+            near.append(np.nextafter(near[-1], 0.0))
+        up = np.nextafter(d2max, np.inf)
+        for _ in range(50):
+            near.append(up)
+            up = np.nextafter(up, np.inf)
+        d2 = np.concatenate([np.array(near), rng.uniform(0.0, 2.0 * cutoff * cutoff, 20000)])
+        assert ((d2 <= d2max) == (np.sqrt(d2) < cutoff)).all()
+    assert lib.kmcb200_cutoff_d2max(0.0) < 0.0 and lib.kmcb200_cutoff_d2max(-1.0) < 0.0
