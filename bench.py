@@ -271,6 +271,43 @@ def pcg_fixed_iterations(kmc, ctx, s, rank, world, dist, iters=60, solves=3):
     return out
 
 
+def kirchhoff_chain(kmc, ctx, name, peak):
+    """BASELINE config 3's split-sparse leg (dist_iterative_test/main_test_cg_split.cpp shape): the Kirchhoff / current
+    chain on a stand-in lattice -- CB-edge solve, T_neighbor + WKB tunnel block assembly, 100-iteration split-sparse
+    Jacobi-PCG (the reference's fixed count, current_solver_gpu.cu:1456) and I_macro -- plus the split SpMV alone.
+    Constants as src/kmc_main.cpp:294-302."""
+    import torch
+    s, desc = build_workload(kmc, name)
+    p = kmc.parse_parameters(PARAM_5NM)
+    dev = kmc.DeviceKMC(s, ctx=ctx)
+    dev.field_solve()
+    cb = ctx.empty_d(s.N, 0.0)
+    t0 = time.perf_counter()
+    it_cb = ctx.update_CB_edge(dev.K, s.N, s.N_left, s.N_right, dev.element, s.metals, s.Vd, s.high_G, s.low_G, cb)
+    torch.cuda.synchronize()
+    cb_ms = 1e3 * (time.perf_counter() - t0)
+    T = ctx.initialize_sparsity_T(dev.element, dev.x, dev.y, dev.z, s.nn_dist, s.N_left, s.N_left, int(p.num_layers_contact))
+    loop_G, high_G, low_G = s.high_G * 10000000, s.high_G * 100000, s.low_G
+    G0, m_e, V0 = 2 * 3.8612e-5 * 1e-5, float(p.m_r) * 9.11e-31, float(p.V0)
+    V = ctx.empty_d(T.N_atom + 1, 0.0)
+    chain = lambda: ctx.update_power_sparse(T, dev.element, dev.charge, cb, s.metals, s.Vd, high_G, low_G, loop_G, G0, m_e, V0, V)
+    im, it = chain()
+    chain_ms = time_ms(torch, chain, 2)
+    asm_ms = time_ms(torch, lambda: ctx.assemble_T(T, dev.element, dev.charge, cb, s.metals, s.Vd, high_G, low_G, loop_G, m_e, V0), 2)
+    T.refresh()
+    xv, yv = ctx.empty_d(T.N_atom + 1, 1.0), ctx.empty_d(T.N_atom + 1, 0.0)
+    spmv_ms = time_ms(torch, lambda: ctx.tmat_spmv(T, xv, yv), 10)
+    spmv_bytes = 12.0 * (T.nnz + T.tunnel_nnz) + 20.0 * (T.N_atom + 1) + 16.0 * T.n_tunnel
+    out = {"workload": desc, "N_atom": int(T.N_atom), "T_neighbor_nnz": int(T.nnz), "tunnel_points": int(T.n_tunnel),
+           "tunnel_nnz": int(T.tunnel_nnz), "cb_edge_solve_ms": cb_ms, "cb_edge_iterations": int(it_cb),
+           "assemble_T_ms": asm_ms, "chain_ms_assemble_plus_100_iterations_plus_imacro": chain_ms,
+           "ms_per_split_sparse_pcg_iteration": (chain_ms - asm_ms) / max(it, 1), "pcg_iterations": int(it),
+           "split_spmv_ms": spmv_ms, "split_spmv_GBs": spmv_bytes / (spmv_ms * 1e-3) / 1e9,
+           "split_spmv_frac_of_hbm_peak": spmv_bytes / (spmv_ms * 1e-3) / 1e9 / peak, "I_macro_A": float(im)}
+    T.close(); dev.ev.close(); dev.K.close()
+    return out
+
+
 def run_extras(args, kmc, ctx, rank, world, dist, peak):
     """Other BASELINE.json configurations, measured outside the headline region.  Rank 0 alone runs
     the single-GPU ones; the field-solve scaling entry uses all ranks."""
@@ -324,6 +361,13 @@ def run_extras(args, kmc, ctx, rank, world, dist, peak):
                                     "cg_iterations": dh.last_cg_iterations, "events": ne, "charged_sources": q,
                                     "us_per_event": 1e3 * dh.events_ms_total / max(ne, 1)}
             dh.ev.close(); dh.K.close(); del dh
+        # ---- config 3, split-sparse leg: Kirchhoff chain with its tunnel block (O(tunnel points^2) non-zeros)
+        for wname in ("5nm", "standin4x4_brick"):
+            try:
+                torch.cuda.empty_cache()
+                extras.setdefault("split_sparse_pcg", []).append(kirchhoff_chain(kmc, ctx, wname, peak))
+            except Exception as e:  # never lose the headline line to an auxiliary measurement
+                extras.setdefault("split_sparse_pcg", []).append({"workload": wname, "error": repr(e)[:300]})
     if world > 1:
         dist.barrier()
     # ---- config 4: >= 10 M-site lattice, strong scaling of the field solve's PCG (the north_star's 0.7 target)
