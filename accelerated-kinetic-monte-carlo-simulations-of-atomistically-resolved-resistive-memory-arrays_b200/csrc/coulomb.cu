@@ -237,6 +237,7 @@ __global__ void __launch_bounds__(CT) coulomb_cell_kernel(const double *__restri
     const bool in_cell = tpos < cell_tstart[c + 1];
     const int i = in_cell ? titems[tpos] : -1;
     const bool active = in_cell && i >= row_start && i < row_start + row_count;
+    if (!__syncthreads_or((int)active)) return;  // row-sharded call: none of this CTA's targets belongs to this rank
     double xi = 0, yi = 0, zi = 0;
     if (active) { xi = x[i]; yi = y[i]; zi = z[i]; }
     const int ls = list_start[c], le = list_start[c + 1];
