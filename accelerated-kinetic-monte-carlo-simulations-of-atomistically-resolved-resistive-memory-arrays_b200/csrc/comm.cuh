@@ -106,7 +106,10 @@ __device__ __forceinline__ unsigned long long kmc_load_relaxed_sys(const unsigne
     asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-// 16-byte cell of the fence-free dot exchange (the LL idea of NCCL: data and sequence number share an 8-byte store)
+// 16-byte cell of the fence-free dot exchange (the LL idea of NCCL: data and sequence number share an 8-byte store).
+// The cell carries the low 32 bits of the 64-bit dot sequence number.  A stale cell could only be mistaken for a fresh
+// one if it had last been written exactly 2^32 dots earlier; every cell of a parity is rewritten at least once per solve
+// (the two setup dots use both cell rows), i.e. every few hundred dots, so that cannot happen.
 __device__ __forceinline__ void kmc_ll_store(uint4 *cell, double v, unsigned seq32) {
     const unsigned long long b = (unsigned long long)__double_as_longlong(v);
     asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(cell), "r"((unsigned)b), "r"(seq32),
