@@ -173,7 +173,11 @@ def build(name: str):
         w = crossbar_standin(7, 7, order=order, Vd=5.0, rnd_seed=5, vacancy_concentration=0.25)
         return w, (f"synthetic high-vacancy lattice: 7x7 lateral tiling of the shipped 5nm cell, N={w.N}, 25 % oxygen "
                    f"vacancies, Vd=5, site order '{order}'")
-    t = {"standin8x8": 8, "standin4x4": 4, "standin2x2": 2, "standin16x16": 16}[base]
+    import re
+    m = re.fullmatch(r"standin(\d+)x(\d+)", base)
+    if not m or m.group(1) != m.group(2):
+        raise ValueError(f"unknown workload '{name}'")
+    t = int(m.group(1))
     w = crossbar_standin(t, t, order=order, Vd=15.0, rnd_seed=32)
     note = {"file": "site order 'file' (tile images site-major: the 5nm file's block structure, wide K bandwidth)",
             "brick": "site order 'brick' (bandwidth-minimised: interior sites grouped in 12.5 A cubes, contacts "

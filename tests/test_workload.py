@@ -52,3 +52,21 @@ def test_workload_module_does_not_load_the_product():
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
     assert out.returncode == 0, out.stderr
     assert out.stdout.strip() == "37650"
+
+
+def test_workload_names(kmc, orc):
+    """bench.py and the CPU arm parse 'standinTxT[_order]' the same way and reject anything else"""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    from oracle import workload
+    assert bench.standin_tiles("standin24x24") == 24 and bench.standin_tiles("standin2x2") == 2
+    for bad in ("standin2x3", "standin", "standinx", "other4x4"):
+        with pytest.raises(ValueError):
+            bench.standin_tiles(bad)
+    with pytest.raises(ValueError):
+        workload.build("standin2x3_brick")
+    w, desc = workload.build("standin3x3_brick")
+    s, desc2 = bench.build_workload(kmc, "standin3x3_brick")
+    _same(w, s)
+    assert "3x3" in desc2 and str(s.N) in desc2
