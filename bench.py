@@ -315,37 +315,51 @@ def run_extras(args, kmc, ctx, rank, world, dist, peak):
     extras = {}
     t_begin = time.perf_counter()
     if rank == 0:
+        def guarded(key, fn):
+            """an auxiliary measurement must never cost the headline line (rank 0 always reaches the barrier below)"""
+            try:
+                torch.cuda.empty_cache()
+                extras[key] = fn()
+            except Exception as e:
+                extras[key] = {"error": repr(e)[:300]}
+
         # ---- config 1: the shipped 5 nm device, steady-state KMC steps/s (the only number the reference publishes: ~87/s)
-        s5, _ = build_workload(kmc, "5nm")
-        d5 = kmc.DeviceKMC(s5, ctx=ctx)
-        for _ in range(3):
-            d5.superstep()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        nst = 200
-        for _ in range(nst):
-            d5.superstep()
-        torch.cuda.synchronize()
-        ms5 = 1e3 * (time.perf_counter() - t0) / nst
-        extras["5nm_device"] = {"workload": workload_desc("5nm", s5.N, s5.N_left), "kmc_steps_per_sec": 1e3 / ms5,
-                                "ms_per_step": ms5, "supersteps_timed": nst, "vs_baseline": (1e3 / ms5) / 87.0,
-                                "baseline": "87 steps/s steady state, 1 MI250X GCD (reference output1_0.txt)"}
-        d5.ev.close(); d5.K.close(); del d5
+        def cfg_5nm():
+            s5, _ = build_workload(kmc, "5nm")
+            d5 = kmc.DeviceKMC(s5, ctx=ctx)
+            for _ in range(3):
+                d5.superstep()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            nst = 200
+            for _ in range(nst):
+                d5.superstep()
+            torch.cuda.synchronize()
+            ms5 = 1e3 * (time.perf_counter() - t0) / nst
+            d5.ev.close(); d5.K.close()
+            return {"workload": workload_desc("5nm", s5.N, s5.N_left), "kmc_steps_per_sec": 1e3 / ms5,
+                    "ms_per_step": ms5, "supersteps_timed": nst, "vs_baseline": (1e3 / ms5) / 87.0,
+                    "baseline": "87 steps/s steady state, 1 MI250X GCD (reference output1_0.txt)"}
+        guarded("5nm_device", cfg_5nm)
+
         # ---- config 3: exported Poisson CSR + Jacobi-PCG at the dist_iterative_test/main_test_cg.cpp:182-207 shapes
         #      (sub-tilings of the stand-in: K after step-0 assembly, x0 = 0, fixed 60 iterations)
-        shapes = []
-        for name, want in (("5nm", "7 302 x 186 684 .. closest shipped: 36 498 rows"), ("standin2x2_brick", "70 630 / 1 719 652"),
-                           ("standin4x4_brick", "403 605 / 10 007 089"), ("standin8x8_brick", "1 632 355 / 41 208 963")):
-            if name == "standin8x8_brick" and args.workload == "standin8x8_brick":
-                continue   # that shape is the headline's own roofline block
-            sw, _ = build_workload(kmc, name)
-            r = pcg_fixed_iterations(kmc, ctx, sw, 0, 1, None)
-            r["reference_shape_rows_nnz"] = want
-            r["frac_of_hbm_peak"] = r["GBs_per_gpu"] / peak
-            shapes.append(r)
-        extras["exported_csr_pcg"] = shapes
+        def cfg_exported_csr():
+            shapes = []
+            for name, want in (("5nm", "7 302 x 186 684 .. closest shipped: 36 498 rows"), ("standin2x2_brick", "70 630 / 1 719 652"),
+                               ("standin4x4_brick", "403 605 / 10 007 089"), ("standin8x8_brick", "1 632 355 / 41 208 963")):
+                if name == "standin8x8_brick" and args.workload == "standin8x8_brick":
+                    continue   # that shape is the headline's own roofline block
+                sw, _ = build_workload(kmc, name)
+                r = pcg_fixed_iterations(kmc, ctx, sw, 0, 1, None)
+                r["reference_shape_rows_nnz"] = want
+                r["frac_of_hbm_peak"] = r["GBs_per_gpu"] / peak
+                shapes.append(r)
+            return shapes
+        guarded("exported_csr_pcg", cfg_exported_csr)
+
         # ---- config 5: ~2 M-site high-vacancy lattice (charge sum + rate list + event selection stressed)
-        if args.workload != "highvac7x7_brick":
+        def cfg_highvac():
             sh, desc = build_workload(kmc, "highvac7x7_brick")
             dh = kmc.DeviceKMC(sh, ctx=ctx)
             dh.superstep()
@@ -356,11 +370,14 @@ def run_extras(args, kmc, ctx, rank, world, dist, peak):
             torch.cuda.synchronize()
             msh = 1e3 * (time.perf_counter() - t0)
             q, tests, inr = ctx.poisson_stats()
-            extras["highvac7x7"] = {"workload": desc, "ms_per_step": msh, "kmc_steps_per_sec": 1e3 / msh,
-                                    "field_solve_ms": dh.field_ms_total, "events_ms": dh.events_ms_total,
-                                    "cg_iterations": dh.last_cg_iterations, "events": ne, "charged_sources": q,
-                                    "us_per_event": 1e3 * dh.events_ms_total / max(ne, 1)}
-            dh.ev.close(); dh.K.close(); del dh
+            out = {"workload": desc, "ms_per_step": msh, "kmc_steps_per_sec": 1e3 / msh,
+                   "field_solve_ms": dh.field_ms_total, "events_ms": dh.events_ms_total,
+                   "cg_iterations": dh.last_cg_iterations, "events": ne, "charged_sources": q,
+                   "us_per_event": 1e3 * dh.events_ms_total / max(ne, 1)}
+            dh.ev.close(); dh.K.close()
+            return out
+        if args.workload != "highvac7x7_brick":
+            guarded("highvac7x7", cfg_highvac)
         # ---- config 3, split-sparse leg: Kirchhoff chain with its tunnel block (O(tunnel points^2) non-zeros)
         for wname in ("5nm", "standin4x4_brick"):
             try:
